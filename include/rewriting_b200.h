@@ -1,0 +1,152 @@
+/* rewriting_b200.h — the C-ABI drop-in boundary of librw_b200.so.
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t, returns
+ * 0 on success or a negative rw_status (never throws, never allocates device
+ * memory: scratch is a caller-provided workspace), and runs asynchronously on the
+ * given stream.  Pointers are borrowed; the caller (PyTorch in the shipped host
+ * code) owns all storage.  This is the surface the reference's two pybind11
+ * extension modules plus its library-call "kernels" are replaced by:
+ *
+ *   reference interface (file:line, relative to davidbau/rewriting)      -> entry point here
+ *   -------------------------------------------------------------------------------------------
+ *   fused.fused_bias_act(input,bias,refer,act,grad,alpha,scale)
+ *       utils/stylegan2/op/fused_bias_act.cpp:11-21                        -> rw_fused_bias_act
+ *   upfirdn2d_op.upfirdn2d(input,kernel,up_x,up_y,down_x,down_y,pads)
+ *       utils/stylegan2/op/upfirdn2d.cpp:4-22                              -> rw_upfirdn2d
+ *   ApplyStyle  style[:,:,None,None]*fmap  utils/stylegan2/models.py:616-620 -> rw_prep_keys
+ *   DemodulatedConv2dF.forward (F.conv2d / F.conv_transpose2d + demod)
+ *       utils/stylegan2/models.py:313-329                                  -> rw_prep_weights,
+ *                                                                              rw_demod,
+ *                                                                              rw_modconv_fwd,
+ *                                                                              rw_modconv_up_fwd
+ *   BlurF -> NoiseInjectionF -> FusedLeakyReLUF of an upsampling StyledConv
+ *       utils/stylegan2/models.py:275-281,535-546,622-626                  -> rw_blur_up_act
+ *   NoiseInjectionF.forward  utils/stylegan2/models.py:539-546             -> rw_add_noise
+ *   ToRGBF.forward           utils/stylegan2/models.py:639-655             -> rw_torgb
+ *   autograd of the conv (dgrad / wgrad)                                    -> rw_modconv_fwd on
+ *                                                                              gradient planes,
+ *                                                                              rw_conv_wgrad
+ *   RunningSecondMoment.add -> mom2.addbmm_(a[:,:,None], a[:,None,:])
+ *       utils/runningstats.py:1086-1097,1181-1190                          -> rw_split_rows,
+ *                                                                              rw_second_moment_accum
+ *   projected_conv(weight, direction)  rewrite/ganrewrite.py:806-813       -> rw_project_rank
+ *   ProgressiveGanRewriter.insert hot loop rewrite/ganrewrite.py:279-294   -> rw_insert_loop
+ *
+ * Layout vocabulary
+ *   key planes  : the style-modulated key k = style*x as two bf16 planes (hi, lo; k ~= hi+lo)
+ *                 in "padded-flat" channels-last order: row index = (b*(H+1) + y)*(W+1) + x,
+ *                 y in [0,H], x in [0,W]; row H and column W are zero.  rows = B*(H+1)*(W+1).
+ *   weight planes: scale*W as bf16 hi/lo, [Cout][tap][Cin] (tap = u*3+v) — or [Cin][tap'][Cout]
+ *                 with flipped taps for dgrad.
+ */
+#ifndef REWRITING_B200_H_
+#define REWRITING_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* rw_stream_t; /* == cudaStream_t */
+
+enum rw_status {
+  RW_STATUS_OK = 0,
+  RW_STATUS_BAD_ARG = -1,
+  RW_STATUS_CUDA = -2,
+  RW_STATUS_NO_DRIVER_SYMBOL = -3,
+  RW_STATUS_UNSUPPORTED = -4
+};
+
+/* ---- library ---- */
+int rw_version(void);
+const char* rw_last_error(void);
+int rw_set_device(int device);
+int rw_device_sm_count(void);
+
+/* ---- operand preparation ---- */
+int rw_prep_keys(const float* x, const float* style, int B, int C, int H, int W, void* kp_hi,
+                 void* kp_lo, float* k_out, rw_stream_t stream);
+int rw_split_rows(const float* a, long long n, void* hi, void* lo, rw_stream_t stream);
+int rw_prep_weights(const float* w, int Cout, int Cin, float scale, int transpose_io,
+                    int flip_taps, void* wt_hi, void* wt_lo, float* wsq, rw_stream_t stream);
+int rw_demod(const float* style, const float* wsq, int B, int Cout, int Cin, float eps,
+             float* demod, rw_stream_t stream);
+
+/* ---- fused modulated 3x3 convolution (tcgen05) ---- */
+/* out[b,o,y,x] = act( conv3x3(k, scale*W)[b,o,y,x] * scale_bo[b,o] + noise_w*noise[b,y*W+x] + bias[o] )
+ * scale_bo / noise / bias may be NULL; act: 0 none, 1 leaky_relu(0.2)*sqrt(2). */
+int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                   const float* scale_bo, const float* noise, long long noise_bstride,
+                   float noise_w, const float* bias, int act, int B, int Cin, int Cout, int H,
+                   int W, float* out, rw_stream_t stream);
+/* t[b,o,:,:] = conv_transpose2d(k, (scale*W)^T, stride 2, pad 0)[b,o] * scale_bo[b,o]; out is
+ * [B,Cout,2H+1,2W+1].  Four polyphase launches, exact algorithmic FLOPs. */
+int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                      const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
+                      rw_stream_t stream);
+/* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */
+int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
+                   const float* noise, long long noise_bstride, float noise_w, const float* bias,
+                   int act, float* y, rw_stream_t stream);
+int rw_add_noise(const float* x, const float* noise, long long noise_bstride, float noise_w,
+                 int B, int C, int HW, float* y, rw_stream_t stream);
+int rw_torgb(const float* x, const float* style, const float* w, const float* bias,
+             const float* skip, int B, int C, int H, int W, float scale, float* out,
+             rw_stream_t stream);
+
+/* ---- operator-level ops of the reference ---- */
+int rw_fused_bias_act(const float* x, const float* bias, const float* ref, int act, int grad,
+                      float alpha, float scale, long long n, int step_b, int size_b, float* y,
+                      rw_stream_t stream);
+int rw_upfirdn2d(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
+                 int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                 int pad_y0, int pad_y1, float* out, int out_h, int out_w, rw_stream_t stream);
+
+/* ---- key second moment / weight gradient (tcgen05 col-GEMM) ---- */
+size_t rw_gram_workspace_bytes(int Cm, int Cn, long long rows, int ntaps);
+/* mom2[C,C] += sum_r a_r a_r^T over `rows` rows of the hi/lo planes [rows][C] */
+int rw_second_moment_accum(const void* hi, const void* lo, long long rows, int C, float* mom2,
+                           void* workspace, size_t workspace_bytes, rw_stream_t stream);
+/* dW[o][tap][i] = sum_p G[p,o] * K[p + shift(tap), i]  for a 3x3 conv over the padded-flat grid
+ * (up=0) or the conv_transpose phases (up=1: G planes are given per phase, see host code). */
+int rw_conv_wgrad(const void* g_hi, const void* g_lo, const void* kp_hi, const void* kp_lo,
+                  long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
+                  size_t workspace_bytes, rw_stream_t stream);
+
+/* ---- rank-r edit ---- */
+/* out = base + sign * P_d(w);  P_d(w)[o,:,t] = sum_r (w[o,:,t] . d_r) d_r;  base may be NULL */
+int rw_project_rank(const float* w, const float* base, const float* d, int rank, int Cout,
+                    int Cin, int taps, float sign, float* out, rw_stream_t stream);
+
+typedef struct rw_insert_args {
+  float* W;               /* [Cout,Cin,3,3], updated in place */
+  float* m;               /* Adam exp_avg     */
+  float* v;               /* Adam exp_avg_sq  */
+  const float* w_ortho;   /* W0 - P_d(W0) or NULL (low_rank_insert off) */
+  const float* d;         /* [rank,Cin] orthonormal rows */
+  const float* key_cl;    /* key crop, zero-bordered channels-last [B][h+2][w+2][Cin] */
+  const float* style;     /* [B,Cin] */
+  const float* target;    /* goal activations v* [B,Cout,h,w] */
+  const float* noise;     /* [B,h*w] or NULL */
+  const float* bias;      /* [Cout] or NULL */
+  float* loss_out;        /* [nsteps,Cout] per-channel sums of |v*-y| */
+  float noise_w, lr, beta1, beta2, eps;
+  int rank, B, Cin, Cout, h, w;
+  int has_noise_act;      /* 1: target = dconv->noise->activate, 0: dconv only */
+  int it0, nsteps, niter_total, piter, project_gradient;
+} rw_insert_args;
+int rw_insert_loop(const rw_insert_args* args, rw_stream_t stream);
+
+/* ---- bring-up hooks (tests/tools only) ---- */
+int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                     int rows, int K, int N, float* out, rw_stream_t stream);
+int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                     int rows, int Cm, int Cn, int lbo_bytes, int sbo_bytes, float* out,
+                     void* workspace, size_t workspace_bytes, rw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REWRITING_B200_H_ */

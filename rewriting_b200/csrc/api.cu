@@ -1,0 +1,430 @@
+// api.cu — the extern "C" boundary declared in include/rewriting_b200.h plus the
+// small host-side utilities shared by the kernel translation units.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/rewriting_b200.h"
+#include "rw_common.cuh"
+#include "rw_kernels.h"
+
+namespace rw {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return RW_OK;
+  set_last_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return RW_ERR_CUDA;
+}
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return RW_ERR_NO_DRIVER_SYMBOL;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 0xF) != 0 || (row_stride_bytes & 0xF) != 0) {
+    set_last_error("TMA operand must be 16-byte aligned (ptr=%p stride=%llu)", base,
+                   (unsigned long long)row_stride_bytes);
+    return RW_ERR_BAD_ARG;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (inner=%llu outer=%llu box=%ux%u)",
+                   (int)r, (unsigned long long)inner, (unsigned long long)outer, box_inner,
+                   box_outer);
+    return RW_ERR_CUDA;
+  }
+  return RW_OK;
+}
+
+// split heuristic shared by the workspace query and the launches
+static int gram_splits(int tiles, long long rows, int ntaps) {
+  const long long total_rb = (rows + 63) / 64;
+  const int sms = 148;
+  long long s = (sms + static_cast<long long>(tiles) * ntaps - 1) / (static_cast<long long>(tiles) * ntaps);
+  if (s > total_rb) s = total_rb;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return static_cast<int>(s);
+}
+
+}  // namespace rw
+
+using namespace rw;
+
+extern "C" {
+
+int rw_version(void) { return 100; }
+const char* rw_last_error(void) { return g_err; }
+int rw_set_device(int device) { return check_cuda(cudaSetDevice(device), "cudaSetDevice"); }
+int rw_device_sm_count(void) { return device_sm_count(); }
+
+int rw_prep_keys(const float* x, const float* style, int B, int C, int H, int W, void* kp_hi,
+                 void* kp_lo, float* k_out, rw_stream_t stream) {
+  if (!x || !kp_hi || !kp_lo || B < 1 || H < 1 || W < 1) {
+    set_last_error("rw_prep_keys: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return prep_keys_launch(x, style, B, C, H, W, kp_hi, kp_lo, k_out, stream);
+}
+
+int rw_split_rows(const float* a, long long n, void* hi, void* lo, rw_stream_t stream) {
+  if (n == 0) return RW_OK;
+  if (!a || !hi || !lo || n < 0) {
+    set_last_error("rw_split_rows: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return split_rows_launch(a, n, hi, lo, stream);
+}
+
+int rw_prep_weights(const float* w, int Cout, int Cin, float scale, int transpose_io,
+                    int flip_taps, void* wt_hi, void* wt_lo, float* wsq, rw_stream_t stream) {
+  if (!w || !wt_hi || !wt_lo || Cout < 1 || Cin < 1) {
+    set_last_error("rw_prep_weights: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return prep_weights_launch(w, Cout, Cin, scale, transpose_io, flip_taps, wt_hi, wt_lo, wsq,
+                             stream);
+}
+
+int rw_demod(const float* style, const float* wsq, int B, int Cout, int Cin, float eps,
+             float* demod, rw_stream_t stream) {
+  if (!style || !wsq || !demod) {
+    set_last_error("rw_demod: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return demod_launch(style, wsq, B, Cout, Cin, eps, demod, stream);
+}
+
+int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                   const float* scale_bo, const float* noise, long long noise_bstride,
+                   float noise_w, const float* bias, int act, int B, int Cin, int Cout, int H,
+                   int W, float* out, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !out || B < 1) {
+    set_last_error("rw_modconv_fwd: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Hp = H + 1;
+  p.Wp = W + 1;
+  p.Hv = H;
+  p.Wv = W;
+  const long long rows = static_cast<long long>(B) * p.Hp * p.Wp;
+  if (rows > 0x7fffffffLL) {
+    set_last_error("rw_modconv_fwd: too many rows");
+    return RW_ERR_BAD_ARG;
+  }
+  p.rows = static_cast<int>(rows);
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.ntaps = 9;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      p.tap_shift[u * 3 + v] = (u - 1) * p.Wp + (v - 1);
+      p.tap_kofs[u * 3 + v] = (u * 3 + v) * Cin;
+    }
+  p.scale_bo = scale_bo;
+  p.bias = bias;
+  p.noise = noise;
+  p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w;
+  p.act = act;
+  p.out = out;
+  p.out_sb = static_cast<long long>(Cout) * H * W;
+  p.out_sc = static_cast<long long>(H) * W;
+  p.out_sy = W;
+  p.out_sx = 1;
+  return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
+}
+
+int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                      const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
+                      rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !t_out || B < 1) {
+    set_last_error("rw_modconv_up_fwd: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  // conv_transpose2d(stride 2, pad 0, k 3): out[2m+a, 2n+b] gathers
+  //   a == 0: (u=0, in row m), (u=2, in row m-1);  a == 1: (u=1, in row m)   (same along x)
+  // over the padded-flat grid every phase is a row-GEMM with <= 4 shifted taps.
+  const int Hp = H + 1, Wp = W + 1;
+  const int Ht = 2 * H + 1, Wt = 2 * W + 1;
+  const long long rows = static_cast<long long>(B) * Hp * Wp;
+  if (rows > 0x7fffffffLL) {
+    set_last_error("rw_modconv_up_fwd: too many rows");
+    return RW_ERR_BAD_ARG;
+  }
+  for (int a = 0; a < 2; ++a) {
+    for (int b = 0; b < 2; ++b) {
+      ConvTcParams p;
+      memset(&p, 0, sizeof(p));
+      p.Hp = Hp;
+      p.Wp = Wp;
+      p.Hv = Hp - a;
+      p.Wv = Wp - b;
+      p.rows = static_cast<int>(rows);
+      p.Cin = Cin;
+      p.Cout = Cout;
+      int us[2], dys[2], nu;
+      int vs[2], dxs[2], nv;
+      if (a == 0) { nu = 2; us[0] = 0; dys[0] = 0; us[1] = 2; dys[1] = -1; }
+      else        { nu = 1; us[0] = 1; dys[0] = 0; }
+      if (b == 0) { nv = 2; vs[0] = 0; dxs[0] = 0; vs[1] = 2; dxs[1] = -1; }
+      else        { nv = 1; vs[0] = 1; dxs[0] = 0; }
+      p.ntaps = 0;
+      for (int iu = 0; iu < nu; ++iu)
+        for (int iv = 0; iv < nv; ++iv) {
+          p.tap_shift[p.ntaps] = dys[iu] * Wp + dxs[iv];
+          p.tap_kofs[p.ntaps] = (us[iu] * 3 + vs[iv]) * Cin;
+          ++p.ntaps;
+        }
+      p.scale_bo = scale_bo;
+      p.out = t_out + static_cast<long long>(a) * Wt + b;
+      p.out_sb = static_cast<long long>(Cout) * Ht * Wt;
+      p.out_sc = static_cast<long long>(Ht) * Wt;
+      p.out_sy = 2LL * Wt;
+      p.out_sx = 2;
+      int rc = conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
+      if (rc) return rc;
+    }
+  }
+  return RW_OK;
+}
+
+int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
+                   const float* noise, long long noise_bstride, float noise_w, const float* bias,
+                   int act, float* y, rw_stream_t stream) {
+  if (!t || !kernel4x4 || !y) {
+    set_last_error("rw_blur_up_act: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return blur_up_act_launch(t, B, C, Hin, Win, kernel4x4, noise, noise_bstride, noise_w, bias, act,
+                            y, stream);
+}
+
+int rw_add_noise(const float* x, const float* noise, long long noise_bstride, float noise_w,
+                 int B, int C, int HW, float* y, rw_stream_t stream) {
+  if (!x || !noise || !y) {
+    set_last_error("rw_add_noise: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return add_noise_launch(x, noise, noise_bstride, noise_w, B, C, HW, y, stream);
+}
+
+int rw_torgb(const float* x, const float* style, const float* w, const float* bias,
+             const float* skip, int B, int C, int H, int W, float scale, float* out,
+             rw_stream_t stream) {
+  if (!x || !style || !w || !bias || !out || C > 4096) {
+    set_last_error("rw_torgb: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return torgb_launch(x, style, w, bias, skip, B, C, H, W, scale, out, stream);
+}
+
+int rw_fused_bias_act(const float* x, const float* bias, const float* ref, int act, int grad,
+                      float alpha, float scale, long long n, int step_b, int size_b, float* y,
+                      rw_stream_t stream) {
+  if (n == 0) return RW_OK;
+  if (!x || !y || n < 0) {
+    set_last_error("rw_fused_bias_act: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return bias_act_launch(x, bias, ref, act, grad, alpha, scale, n, step_b, size_b, y, stream);
+}
+
+int rw_upfirdn2d(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
+                 int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                 int pad_y0, int pad_y1, float* out, int out_h, int out_w, rw_stream_t stream) {
+  if (!in || !kernel || !out || up_x < 1 || up_y < 1 || down_x < 1 || down_y < 1) {
+    set_last_error("rw_upfirdn2d: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return upfirdn2d_launch(in, kernel, major, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y,
+                          pad_x0, pad_x1, pad_y0, pad_y1, out, out_h, out_w, stream);
+}
+
+size_t rw_gram_workspace_bytes(int Cm, int Cn, long long rows, int ntaps) {
+  if (Cm < 128 || Cn < 128 || ntaps < 1) return 0;
+  const int mt = Cm / 128, nt = Cn / 128;
+  const int tiles_full = mt * nt;
+  // the symmetric path uses fewer tiles -> more splits; size for the larger of the two
+  const int tiles_sym = (Cm == Cn) ? mt * (mt + 1) / 2 : tiles_full;
+  const int s1 = gram_splits(tiles_full, rows, ntaps);
+  const int s2 = gram_splits(tiles_sym, rows, ntaps);
+  const int s = s1 > s2 ? s1 : s2;
+  return static_cast<size_t>(s) * Cm * static_cast<size_t>(Cn) * ntaps * sizeof(float);
+}
+
+int rw_second_moment_accum(const void* hi, const void* lo, long long rows, int C, float* mom2,
+                           void* workspace, size_t workspace_bytes, rw_stream_t stream) {
+  if (rows == 0) return RW_OK;
+  if (!hi || !lo || !mom2 || !workspace || rows < 0 || rows > 0x7fffffffLL || C % 128 != 0) {
+    set_last_error("rw_second_moment_accum: bad argument (rows=%lld C=%d)", rows, C);
+    return RW_ERR_BAD_ARG;
+  }
+  GramTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = static_cast<int>(rows);
+  p.rows_a = p.rows_b = static_cast<int>(rows);
+  p.Cm = p.Cn = C;
+  p.ntaps = 1;
+  p.upper_only = 1;
+  const int mt = C / 128;
+  p.splits = gram_splits(mt * (mt + 1) / 2, rows, 1);
+  p.ldp = C;
+  p.partial = static_cast<float*>(workspace);
+  const size_t need = static_cast<size_t>(p.splits) * C * C * sizeof(float);
+  if (workspace_bytes < need) {
+    set_last_error("rw_second_moment_accum: workspace %zu < %zu bytes", workspace_bytes, need);
+    return RW_ERR_BAD_ARG;
+  }
+  int rc = gram_tc_launch(p, hi, lo, hi, lo, stream);
+  if (rc) return rc;
+  return reduce_partials_launch(p.partial, p.splits, C, C, p.ldp, mom2, C, /*accumulate=*/1,
+                                /*mirror_upper=*/1, stream);
+}
+
+int rw_conv_wgrad(const void* g_hi, const void* g_lo, const void* kp_hi, const void* kp_lo,
+                  long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
+                  size_t workspace_bytes, rw_stream_t stream) {
+  if (!g_hi || !g_lo || !kp_hi || !kp_lo || !dw_toi || !workspace || rows <= 0 ||
+      rows > 0x7fffffffLL) {
+    set_last_error("rw_conv_wgrad: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  GramTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = static_cast<int>(rows);
+  p.rows_a = p.rows_b = static_cast<int>(rows);
+  p.Cm = Cout;
+  p.Cn = Cin;
+  p.ntaps = 9;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      p.tap_shift_b[u * 3 + v] = (u - 1) * Wp + (v - 1);
+      p.tap_col_ofs[u * 3 + v] = (u * 3 + v) * Cin;
+    }
+  p.upper_only = 0;
+  p.splits = gram_splits((Cout / 128) * (Cin / 128), rows, 9);
+  p.ldp = 9LL * Cin;
+  p.partial = static_cast<float*>(workspace);
+  const size_t need = static_cast<size_t>(p.splits) * Cout * 9 * Cin * sizeof(float);
+  if (workspace_bytes < need) {
+    set_last_error("rw_conv_wgrad: workspace %zu < %zu bytes", workspace_bytes, need);
+    return RW_ERR_BAD_ARG;
+  }
+  int rc = gram_tc_launch(p, g_hi, g_lo, kp_hi, kp_lo, stream);
+  if (rc) return rc;
+  return reduce_partials_launch(p.partial, p.splits, Cout, 9 * Cin, p.ldp, dw_toi, 9LL * Cin,
+                                /*accumulate=*/0, /*mirror_upper=*/0, stream);
+}
+
+int rw_project_rank(const float* w, const float* base, const float* d, int rank, int Cout,
+                    int Cin, int taps, float sign, float* out, rw_stream_t stream) {
+  if (!w || !d || !out) {
+    set_last_error("rw_project_rank: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return project_rank_launch_signed(w, base, d, rank, Cout, Cin, taps, sign, out, stream);
+}
+
+int rw_insert_loop(const rw_insert_args* a, rw_stream_t stream) {
+  if (!a || !a->W || !a->m || !a->v || !a->d || !a->key_cl || !a->style || !a->target ||
+      !a->loss_out || (a->has_noise_act && !a->bias)) {
+    set_last_error("rw_insert_loop: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  InsertLoopParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = a->W; p.m = a->m; p.v = a->v; p.w_ortho = a->w_ortho; p.d = a->d; p.rank = a->rank;
+  p.key = a->key_cl; p.style = a->style; p.target = a->target; p.noise = a->noise;
+  p.noise_w = a->noise_w; p.bias = a->bias;
+  p.B = a->B; p.Cin = a->Cin; p.Cout = a->Cout; p.h = a->h; p.w = a->w;
+  p.has_noise_act = a->has_noise_act;
+  p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+  p.it0 = a->it0; p.niter_total = a->niter_total; p.nsteps = a->nsteps;
+  p.piter = a->piter > 0 ? a->piter : 1;
+  p.project_gradient = a->project_gradient;
+  p.loss_out = a->loss_out;
+  return insert_loop_launch(p, stream);
+}
+
+int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                     int rows, int K, int N, float* out, rw_stream_t stream) {
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.Cin = K; p.Cout = N; p.ntaps = 1;
+  p.Hp = 1; p.Wp = rows; p.Hv = 1; p.Wv = rows;   // one "image" = all rows
+  p.out = out; p.out_sb = 0; p.out_sc = 1; p.out_sy = 0; p.out_sx = N;  // row-major [rows][N]
+  return conv_tc_launch(p, a_hi, a_lo, w_hi, w_lo, K, stream);
+}
+
+int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                     int rows, int Cm, int Cn, int lbo_bytes, int sbo_bytes, float* out,
+                     void* workspace, size_t workspace_bytes, rw_stream_t stream) {
+  GramTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.rows_a = p.rows_b = rows; p.Cm = Cm; p.Cn = Cn; p.ntaps = 1;
+  p.splits = gram_splits((Cm / 128) * (Cn / 128), rows, 1);
+  p.ldp = Cn;
+  p.partial = static_cast<float*>(workspace);
+  const size_t need = static_cast<size_t>(p.splits) * Cm * Cn * sizeof(float);
+  if (workspace_bytes < need) {
+    set_last_error("rw_debug_colgemm: workspace %zu < %zu bytes", workspace_bytes, need);
+    return RW_ERR_BAD_ARG;
+  }
+  if (lbo_bytes > 0 && sbo_bytes > 0) gram_tc_set_desc(lbo_bytes, sbo_bytes);
+  int rc = gram_tc_launch(p, a_hi, a_lo, b_hi, b_lo, stream);
+  if (rc) return rc;
+  return reduce_partials_launch(p.partial, p.splits, Cm, Cn, p.ldp, out, Cn, 0, 0, stream);
+}
+
+}  // extern "C"

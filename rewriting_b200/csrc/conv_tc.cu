@@ -1,0 +1,258 @@
+// conv_tc.cu — tcgen05 implicit-GEMM over the padded-flat key layout ("row-GEMM").
+//
+//   acc[p, o] = sum_{tap} sum_{i} KP[p + shift(tap), i] * Wt[o, tap, i]
+//
+// KP is the style-modulated key  k = style (.) x  (reference: ApplyStyle,
+// utils/stylegan2/models.py:616-620) stored channels-last as two bf16 planes
+// (hi, lo) over a zero-padded flat pixel grid: one image = (H+1) x (W+1)
+// positions, column W and row H are zero, so every 3x3 neighbour (and every
+// conv_transpose phase neighbour) is a plain row shift of the same 2-D matrix
+// and zero padding is implicit.  Wt is scale*W (models.py:315-319) as bf16
+// hi/lo planes [Cout][tap][Cin].  Three MMAs per k-step (hi*hi + lo*hi + hi*lo)
+// reproduce the fp32 conv of the reference to ~2^-17 relative (SURVEY.md §7:
+// single-pass bf16/tf32 fails the 1e-3 pixel tolerance, 3xBF16 passes).
+//
+// Epilogue (fused, per accumulator element) follows DemodulatedConv2dF /
+// NoiseInjectionF / FusedLeakyReLUF (models.py:320-328, 539-546;
+// op/fused_bias_act_kernel.cu:27-47):
+//   y = lrelu(acc * scale[b,o] + noise_w * noise[b, y*W+x] + bias[o], 0.2) * sqrt(2)
+// each term optional, so the same kernel serves the un-fused `dconv` leaf of a
+// nethook-split layer, the conv_transpose phases of an up layer and dgrad.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM
+// alloc), warps 2..5 = epilogue (TMEM -> regs -> global).  Persistent CTAs,
+// 3-stage smem ring, double-buffered TMEM accumulators.
+#include "rw_common.cuh"
+#include "rw_kernels.h"
+
+namespace rw {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // bf16 elements per k-block = one 128B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 3;
+constexpr int kNumThreads = 192;
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int kABytes = BM * BK * 2;   // one plane
+  static constexpr int kBBytes = BN * BK * 2;   // one plane
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Barriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+               const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi,
+               const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  using S = ConvSmem<BN>;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * S::kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int n_tiles = p.Cout / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kb_per_tap = p.Cin / BK;
+  const int num_kb = p.ntaps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_w_hi);
+    tma_prefetch_desc(&map_w_lo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<2 * BN>(&bars->tmem_base);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BN;
+        const int m0 = (tile / n_tiles) * BM;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int arow = m0 + p.tap_shift[t];
+          const int wcol = p.tap_kofs[t];
+          for (int kb = 0; kb < kb_per_tap; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            uint8_t* st = smem + stage * S::kStageBytes;
+            mbar_expect_tx(&bars->full[stage], S::kStageBytes);
+            tma_load_2d(st, &map_a_hi, &bars->full[stage], kb * BK, arow);
+            tma_load_2d(st + S::kABytes, &map_a_lo, &bars->full[stage], kb * BK, arow);
+            tma_load_2d(st + 2 * S::kABytes, &map_w_hi, &bars->full[stage], wcol + kb * BK, n0);
+            tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_w_lo, &bars->full[stage],
+                        wcol + kb * BK, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t da_hi = make_smem_desc(sa, 16, 1024, kSwizzle128B);
+          const uint64_t da_lo = make_smem_desc(sa + S::kABytes, 16, 1024, kSwizzle128B);
+          const uint64_t db_hi = make_smem_desc(sa + 2 * S::kABytes, 16, 1024, kSwizzle128B);
+          const uint64_t db_lo =
+              make_smem_desc(sa + 2 * S::kABytes + S::kBBytes, 16, 1024, kSwizzle128B);
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
+            // smallest terms first, then the dominant hi*hi product
+            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | kk) != 0);
+            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tmem_full[as]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int img = p.Hp * p.Wp;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BM;
+      const int prow = m0 + q * 32 + lane;
+      const int b = prow / img;
+      const int rem = prow - b * img;
+      const int yy = rem / p.Wp;
+      const int xx = rem - yy * p.Wp;
+      const bool valid = (prow < p.rows) && (yy < p.Hv) && (xx < p.Wv);
+      float nz = 0.f;
+      if (valid && p.noise != nullptr) {
+        nz = p.noise_w * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
+                               static_cast<size_t>(yy) * p.Wv + xx);
+      }
+      float* outp = p.out + static_cast<size_t>(b) * p.out_sb + static_cast<size_t>(yy) * p.out_sy +
+                    static_cast<size_t>(xx) * p.out_sx;
+      const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
+
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN + c0) +
+                               (static_cast<uint32_t>(q * 32) << 16);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int o = n0 + c0 + j;
+            float t = __uint_as_float(v[j]);
+            if (scl) t *= __ldg(scl + o);
+            t += nz;
+            if (p.bias) t += __ldg(p.bias + o);
+            if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
+            outp[static_cast<size_t>(o) * p.out_sc] = t;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
+                   const void* w_lo, int wk_total, cudaStream_t stream) {
+  constexpr int BN = 128;
+  if (p.Cin % BK != 0 || p.Cout % BN != 0 || p.ntaps < 1 || p.ntaps > 9 || p.rows <= 0) {
+    set_last_error("conv_tc: unsupported shape Cin=%d Cout=%d ntaps=%d rows=%d", p.Cin, p.Cout,
+                   p.ntaps, p.rows);
+    return RW_ERR_BAD_ARG;
+  }
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, p.Cin, p.rows, (uint64_t)p.Cin * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, p.Cin, p.rows, (uint64_t)p.Cin * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))
+    return rc;
+  if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))
+    return rc;
+
+  using S = ConvSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+                    "conv_tc smem attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int n_tiles = p.Cout / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  int grid = device_sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+  conv_tc_kernel<BN><<<grid, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  return check_cuda(cudaGetLastError(), "conv_tc launch");
+}
+
+}  // namespace rw

@@ -1,0 +1,116 @@
+// rw_kernels.h — internal launch interfaces between the C-ABI (api.cu) and the
+// kernel translation units.  Not part of the public boundary (see
+// include/rewriting_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rw {
+
+// ---------------------------------------------------------------------------
+// row-GEMM (conv_tc.cu)
+// ---------------------------------------------------------------------------
+struct ConvTcParams {
+  int rows;          // padded-flat rows = B * Hp * Wp  (GEMM M)
+  int Cin;           // GEMM K per tap
+  int Cout;          // GEMM N
+  int ntaps;
+  int tap_shift[9];  // row shift applied to the A operand for this tap
+  int tap_kofs[9];   // column offset of this tap inside the weight matrix
+  int Hp, Wp;        // padded grid of one image
+  int Hv, Wv;        // valid output extent inside the padded grid
+  // epilogue
+  const float* scale_bo;  // [B, Cout] per-sample per-channel scale (demod / style) or null
+  const float* bias;      // [Cout] or null
+  const float* noise;     // [B, noise_bstride] or null, indexed y*Wv + x
+  long long noise_bstride;
+  float noise_w;
+  int act;                // 1 -> leaky_relu(0.2) * sqrt(2)
+  float* out;
+  long long out_sb, out_sc, out_sy, out_sx;  // element strides: batch, channel, y, x
+};
+
+int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
+                   const void* w_lo, int wk_total, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// col-GEMM (gram_tc.cu):  out[m, n] = sum_r A[r + shift_a, m] * B[r + shift_b, n]
+// ---------------------------------------------------------------------------
+struct GramTcParams {
+  int rows;            // contraction length (rows r in [0, rows))
+  int rows_a, rows_b;  // allocated rows of the A / B planes (for the TMA bounds)
+  int Cm, Cn;          // channels of A (-> M) and B (-> N)
+  int shift_a, shift_b;
+  int ntaps;              // >= 1; grid.z
+  int tap_shift_b[9];     // extra row shift of the B operand per tap
+  int tap_col_ofs[9];     // column offset of this tap's block inside a partial row
+  int splits;          // row-range splits (partials reduced deterministically afterwards)
+  float* partial;      // [splits][Cm][ldp] fp32 workspace
+  long long ldp;       // leading dimension (elements) of one partial matrix row
+  int upper_only;      // 1: skip tiles strictly below the diagonal (symmetric A==B)
+};
+
+int gram_tc_launch(const GramTcParams& p, const void* a_hi, const void* a_lo, const void* b_hi,
+                   const void* b_lo, cudaStream_t stream);
+
+// out[m*ldo+n] (= or +=) sum_s partial[s][m][n]; optional symmetric mirror of the
+// upper triangle into the lower one.
+int reduce_partials_launch(const float* partial, int splits, int M, int N, long long ldp,
+                           float* out, long long ldo, int accumulate, int mirror_upper,
+                           cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// SIMT kernels (simt.cu)
+// ---------------------------------------------------------------------------
+int prep_keys_launch(const float* x, const float* style, int B, int C, int H, int W, void* kp_hi,
+                     void* kp_lo, float* k_out, cudaStream_t stream);
+int split_rows_launch(const float* a, long long n, void* hi, void* lo, cudaStream_t stream);
+int prep_weights_launch(const float* w, int Cout, int Cin, float scale, int transpose_io,
+                        int flip_taps, void* wt_hi, void* wt_lo, float* wsq, cudaStream_t stream);
+int demod_launch(const float* style, const float* wsq, int B, int Cout, int Cin, float eps,
+                 float* demod, cudaStream_t stream);
+int blur_up_act_launch(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
+                       const float* noise, long long noise_bstride, float noise_w,
+                       const float* bias, int act, float* y, cudaStream_t stream);
+int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
+                     int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
+                     int py1, float* out, int out_h, int out_w, cudaStream_t stream);
+int bias_act_launch(const float* x, const float* bias, const float* ref, int act, int grad,
+                    float alpha, float scale, long long n, int step_b, int size_b, float* y,
+                    cudaStream_t stream);
+int torgb_launch(const float* x, const float* style, const float* w, const float* bias,
+                 const float* skip, int B, int C, int H, int W, float scale, float* out,
+                 cudaStream_t stream);
+int add_noise_launch(const float* x, const float* noise, long long noise_bstride, float noise_w,
+                     int B, int C, int HW, float* y, cudaStream_t stream);
+
+// rewrite (rewrite.cu)
+int project_rank_launch_signed(const float* w, const float* base, const float* d, int rank,
+                               int Cout, int Cin, int taps, float sign, float* out,
+                               cudaStream_t stream);
+void gram_tc_set_desc(int lbo, int sbo);
+
+struct InsertLoopParams {
+  float* W;             // [Cout, Cin, 3, 3] updated in place
+  float* m;             // Adam first moment  (same shape)
+  float* v;             // Adam second moment (same shape)
+  const float* w_ortho; // W0 - P_d(W0), or null when low_rank_insert is off
+  const float* d;       // [rank, Cin] orthonormal rows
+  int rank;
+  const float* key;     // key crop, zero-bordered channels-last [B][h+2][w+2][Cin]
+  const float* style;   // [B, Cin]
+  const float* target;  // [B, Cout, h, w] goal activations v*
+  const float* noise;   // [B, h*w] or null
+  float noise_w;
+  const float* bias;    // [Cout]
+  int B, Cin, Cout, h, w;
+  int has_noise_act;    // 1: target ends after `activate`; 0: ends after dconv
+  float lr, beta1, beta2, eps;
+  int it0, niter_total, nsteps;  // run iterations it0 .. it0+nsteps-1
+  int piter;
+  int project_gradient; // low_rank_gradient
+  float* loss_out;      // [nsteps, Cout] per-channel partial |v*-y| sums
+};
+int insert_loop_launch(const InsertLoopParams& p, cudaStream_t stream);
+
+}  // namespace rw

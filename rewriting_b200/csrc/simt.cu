@@ -1,0 +1,419 @@
+// simt.cu — HBM-bound CUDA-core kernels around the tensor-core path: operand
+// preparation (style modulation + bf16 hi/lo split + NCHW -> padded-flat
+// channels-last), demodulation factors, the up-path blur epilogue, ToRGB, and the
+// two operator-level ops of the reference (`fused_bias_act`, `upfirdn2d`).
+//
+// Reference semantics (cited per kernel) are utils/stylegan2/models.py and
+// utils/stylegan2/op/*.  All kernels are coalesced / vectorised; none uses
+// tensor cores (these are byte-movement bound).
+#include "rw_common.cuh"
+#include "rw_kernels.h"
+
+namespace rw {
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// prep_keys: k = style[b,c] * x[b,c,y,x]   (ApplyStyle, models.py:616-620)
+//   -> optional fp32 NCHW copy (the API-visible key) and bf16 hi/lo planes in
+//   the padded-flat layout  [(b, y in 0..H, x in 0..W)][c]  with zero pad row /
+//   pad column.
+// grid: (ceil(Hp*Wp/32), C/64, B), block 256
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_keys_kernel(const float* __restrict__ x, const float* __restrict__ style, int C, int H, int W,
+                 __nv_bfloat16* __restrict__ kp_hi, __nv_bfloat16* __restrict__ kp_lo,
+                 float* __restrict__ k_out) {
+  __shared__ float tile[64][33];
+  const int Hp = H + 1, Wp = W + 1;
+  const int img = Hp * Wp;
+  const int p0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64;
+  const int b = blockIdx.z;
+  const int t = threadIdx.x;
+  {
+    const int pl = t & 31;
+    const int p = p0 + pl;
+    const int yy = p / Wp, xx = p - yy * Wp;
+    const bool valid = (p < img) && (yy < H) && (xx < W);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cl = (t >> 5) + 8 * i;
+      float v = 0.f;
+      if (valid) {
+        const size_t gi = ((static_cast<size_t>(b) * C + c0 + cl) * H + yy) * W + xx;
+        const float s = style ? __ldg(style + static_cast<size_t>(b) * C + c0 + cl) : 1.f;
+        v = s * __ldg(x + gi);
+        if (k_out) k_out[gi] = v;
+      }
+      tile[cl][pl] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int pl = t >> 3;        // 0..31 position
+    const int cg = (t & 7) * 8;   // 8 channels per thread
+    const int p = p0 + pl;
+    if (p < img) {
+      __align__(16) __nv_bfloat16 h[8];
+      __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(tile[cg + j][pl], h[j], l[j]);
+      const size_t row = static_cast<size_t>(b) * img + p;
+      *reinterpret_cast<uint4*>(kp_hi + row * C + c0 + cg) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(kp_lo + row * C + c0 + cg) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// split_rows: fp32 -> bf16 hi/lo planes, same shape (generic RunningSecondMoment
+// input [N, C], runningstats.py:1086)
+// ---------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ a, long long n,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(a + i4);
+    __align__(8) __nv_bfloat16 h[4];
+    __align__(8) __nv_bfloat16 l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + i4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + i4) = *reinterpret_cast<const uint2*>(l);
+  } else {
+    for (long long i = i4; i < n; ++i) split_bf16(a[i], hi[i], lo[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// prep_weights: W[Cout][Cin][3][3] fp32 -> (scale*W) as bf16 hi/lo planes
+//   transpose_io = 0: Wt[o][tap][i]            (forward conv / conv_transpose)
+//   transpose_io = 1: Wt[i][tap'][o]           (dgrad), tap' = 8 - tap if flip
+// and wsq[o][i] = sum_taps (scale*W)^2   (for demod, models.py:325-327)
+// one thread per (o, i)
+// ---------------------------------------------------------------------------
+__global__ void prep_weights_kernel(const float* __restrict__ w, int Cout, int Cin, float scale,
+                                    int transpose_io, int flip_taps,
+                                    __nv_bfloat16* __restrict__ wt_hi,
+                                    __nv_bfloat16* __restrict__ wt_lo, float* __restrict__ wsq) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin) return;
+  const int o = idx / Cin, i = idx - o * Cin;
+  const float* src = w + static_cast<size_t>(idx) * 9;
+  float ss = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float v = scale * src[tap];
+    ss += v * v;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    size_t dst;
+    if (!transpose_io) {
+      dst = (static_cast<size_t>(o) * 9 + tap) * Cin + i;
+    } else {
+      const int tp = flip_taps ? 8 - tap : tap;
+      dst = (static_cast<size_t>(i) * 9 + tp) * Cout + o;
+    }
+    wt_hi[dst] = h;
+    wt_lo[dst] = l;
+  }
+  if (wsq) wsq[idx] = ss;
+}
+
+// ---------------------------------------------------------------------------
+// demod[b,o] = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)      one warp per (b,o)
+// ---------------------------------------------------------------------------
+__global__ void demod_kernel(const float* __restrict__ style, const float* __restrict__ wsq, int B,
+                             int Cout, int Cin, float eps, float* __restrict__ demod) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * Cout) return;
+  const int b = gw / Cout, o = gw - b * Cout;
+  const float* s = style + static_cast<size_t>(b) * Cin;
+  const float* q = wsq + static_cast<size_t>(o) * Cin;
+  float acc = 0.f;
+  for (int i = lane; i < Cin; i += 32) {
+    const float sv = __ldg(s + i);
+    acc = fmaf(sv * sv, __ldg(q + i), acc);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) demod[gw] = rsqrtf(acc + eps);
+}
+
+// ---------------------------------------------------------------------------
+// blur_up_act: second half of an upsampling StyledConv.
+//   t [B,C,2H+1,2W+1] (conv_transpose output, already demodulated)
+//   y = act( FIR4x4(pad(t,1,1)) + noise_w*noise + bias )          [B,C,2H,2W]
+// (BlurF pad=(1,1): models.py:275-281,468-485; then NoiseInjectionF, FusedLeakyReLUF)
+// block = 32x8 outputs, smem tile with 3-pixel halo.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+blur_up_act_kernel(const float* __restrict__ t, int C, int Ht, int Wt, const float* __restrict__ k4,
+                   const float* __restrict__ noise, long long noise_bstride, float noise_w,
+                   const float* __restrict__ bias, int act, float* __restrict__ y) {
+  constexpr int TX = 32, TY = 8;
+  __shared__ float tile[TY + 3][TX + 3];
+  __shared__ float kf[16];
+  const int Ho = Ht - 1, Wo = Wt - 1;
+  const int bc = blockIdx.z;
+  const int b = bc / C, c = bc - b * C;
+  const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  // upfirdn2d correlates the padded signal with the *flipped* kernel
+  if (tid < 16) kf[tid] = __ldg(k4 + 15 - tid);
+  const float* src = t + static_cast<size_t>(bc) * Ht * Wt;
+  for (int i = tid; i < (TY + 3) * (TX + 3); i += TX * TY) {
+    const int ly = i / (TX + 3), lx = i - ly * (TX + 3);
+    const int iy = oy0 + ly - 1, ix = ox0 + lx - 1;  // pad 1 on the low side
+    float v = 0.f;
+    if (iy >= 0 && iy < Ht && ix >= 0 && ix < Wt) v = __ldg(src + static_cast<size_t>(iy) * Wt + ix);
+    tile[ly][lx] = v;
+  }
+  __syncthreads();
+  const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+  if (ox >= Wo || oy >= Ho) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb)
+      acc = fmaf(tile[threadIdx.y + a][threadIdx.x + bb], kf[a * 4 + bb], acc);
+  if (noise) acc += noise_w * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
+                                    static_cast<size_t>(oy) * Wo + ox);
+  if (bias) acc += __ldg(bias + c);
+  if (act) acc = (acc > 0.f ? acc : 0.2f * acc) * 1.4142135623730951f;
+  y[(static_cast<size_t>(bc) * Ho + oy) * Wo + ox] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// upfirdn2d (generic, minor == 1 as called by the reference):
+//   zero-insert upsample, pad/crop, correlate with flipped kernel, decimate.
+// (op/upfirdn2d.py:152-186 defines the semantics; upfirdn2d_kernel.cu:52-137
+//  is the reference's tiled implementation.)  One thread per output sample.
+// ---------------------------------------------------------------------------
+__global__ void upfirdn2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
+                                 int in_h, int in_w, int kh, int kw, int up_x, int up_y,
+                                 int down_x, int down_y, int px0, int py0, float* __restrict__ out,
+                                 int out_h, int out_w, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % out_w);
+  const long long r = idx / out_w;
+  const int oy = static_cast<int>(r % out_h);
+  const long long mj = r / out_h;
+  const float* src = in + mj * in_h * in_w;
+  float acc = 0.f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int uy = oy * down_y + ky - py0;
+    if (uy < 0 || uy % up_y != 0) continue;
+    const int iy = uy / up_y;
+    if (iy >= in_h) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int ux = ox * down_x + kx - px0;
+      if (ux < 0 || ux % up_x != 0) continue;
+      const int ix = ux / up_x;
+      if (ix >= in_w) continue;
+      acc = fmaf(__ldg(src + static_cast<size_t>(iy) * in_w + ix),
+                 __ldg(kern + (kh - 1 - ky) * kw + (kw - 1 - kx)), acc);
+    }
+  }
+  out[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// bias_act: y = act(x + b[(i/step_b)%size_b]) * scale with the reference's
+// act/grad switch (op/fused_bias_act_kernel.cu:19-49): act 1 = linear,
+// 3 = lrelu(alpha); grad 0 = forward, 1 = gate by sign of `ref`, 2 = zero.
+// ---------------------------------------------------------------------------
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                const float* __restrict__ ref, int act, int grad, float alpha,
+                                float scale, long long n, int step_b, int size_b,
+                                float* __restrict__ y) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    float v = x[i];
+    if (b) v += __ldg(b + (i / step_b) % size_b);
+    const float r = ref ? ref[i] : 0.f;
+    float o;
+    if (grad == 2) {
+      o = 0.f;
+    } else if (act == 3) {
+      const float g = (grad == 1) ? r : v;
+      o = (g > 0.f) ? v : v * alpha;
+    } else {
+      o = v;
+    }
+    y[i] = o * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// torgb: out[b,c,p] = sum_i (scale * w[c,i] * style[b,i]) * x[b,i,p] + bias[c] (+ skip[b,c,p])
+// (ToRGBF + ModulatedConv2d(demodulate=False, k=1): models.py:394-425,628-655)
+// block = 256 pixels of one sample; modulated weights staged in smem.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+torgb_kernel(const float* __restrict__ x, const float* __restrict__ style,
+             const float* __restrict__ w, const float* __restrict__ bias,
+             const float* __restrict__ skip, int C, int HW, float scale, float* __restrict__ out) {
+  extern __shared__ float wm[];  // [3][C]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int ci = i % C;
+    wm[i] = (scale * __ldg(w + i)) * __ldg(style + static_cast<size_t>(b) * C + ci);
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* xb = x + static_cast<size_t>(b) * C * HW + p;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < C; ++i) {
+    const float v = __ldg(xb + static_cast<size_t>(i) * HW);
+    a0 = fmaf(wm[i], v, a0);
+    a1 = fmaf(wm[C + i], v, a1);
+    a2 = fmaf(wm[2 * C + i], v, a2);
+  }
+  float* ob = out + static_cast<size_t>(b) * 3 * HW + p;
+  const float* sb = skip ? skip + static_cast<size_t>(b) * 3 * HW + p : nullptr;
+  a0 += __ldg(bias + 0);
+  a1 += __ldg(bias + 1);
+  a2 += __ldg(bias + 2);
+  if (sb) { a0 += sb[0]; a1 += sb[HW]; a2 += sb[2 * static_cast<size_t>(HW)]; }
+  ob[0] = a0;
+  ob[HW] = a1;
+  ob[2 * static_cast<size_t>(HW)] = a2;
+}
+
+// y[b,c,p] = x[b,c,p] + noise_w * noise[b,p]     (NoiseInjectionF, models.py:535-546)
+__global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                 long long noise_bstride, float noise_w, int C, int HW,
+                                 long long total, float* __restrict__ y) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += stride) {
+    const int p = static_cast<int>(i % HW);
+    const long long b = i / (static_cast<long long>(HW) * C);
+    y[i] = x[i] + noise_w * __ldg(noise + b * noise_bstride + p);
+  }
+}
+
+inline int grid_for(long long n, int threads, int cap = 148 * 16) {
+  long long g = (n + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int prep_keys_launch(const float* x, const float* style, int B, int C, int H, int W, void* kp_hi,
+                     void* kp_lo, float* k_out, cudaStream_t stream) {
+  if (C % 64 != 0) {
+    set_last_error("prep_keys: C=%d must be a multiple of 64", C);
+    return RW_ERR_BAD_ARG;
+  }
+  const int img = (H + 1) * (W + 1);
+  dim3 grid((img + 31) / 32, C / 64, B);
+  prep_keys_kernel<<<grid, 256, 0, stream>>>(x, style, C, H, W,
+                                             static_cast<__nv_bfloat16*>(kp_hi),
+                                             static_cast<__nv_bfloat16*>(kp_lo), k_out);
+  return check_cuda(cudaGetLastError(), "prep_keys launch");
+}
+
+int split_rows_launch(const float* a, long long n, void* hi, void* lo, cudaStream_t stream) {
+  const int threads = 256;
+  const long long n4 = (n + 3) / 4;
+  const int blocks = static_cast<int>((n4 + threads - 1) / threads);
+  split_rows_kernel<<<blocks, threads, 0, stream>>>(a, n, static_cast<__nv_bfloat16*>(hi),
+                                                    static_cast<__nv_bfloat16*>(lo));
+  return check_cuda(cudaGetLastError(), "split_rows launch");
+}
+
+int prep_weights_launch(const float* w, int Cout, int Cin, float scale, int transpose_io,
+                        int flip_taps, void* wt_hi, void* wt_lo, float* wsq, cudaStream_t stream) {
+  const int n = Cout * Cin;
+  prep_weights_kernel<<<(n + 255) / 256, 256, 0, stream>>>(
+      w, Cout, Cin, scale, transpose_io, flip_taps, static_cast<__nv_bfloat16*>(wt_hi),
+      static_cast<__nv_bfloat16*>(wt_lo), wsq);
+  return check_cuda(cudaGetLastError(), "prep_weights launch");
+}
+
+int demod_launch(const float* style, const float* wsq, int B, int Cout, int Cin, float eps,
+                 float* demod, cudaStream_t stream) {
+  const long long warps = static_cast<long long>(B) * Cout;
+  const int threads = 256;
+  const int blocks = static_cast<int>((warps * 32 + threads - 1) / threads);
+  demod_kernel<<<blocks, threads, 0, stream>>>(style, wsq, B, Cout, Cin, eps, demod);
+  return check_cuda(cudaGetLastError(), "demod launch");
+}
+
+int blur_up_act_launch(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
+                       const float* noise, long long noise_bstride, float noise_w,
+                       const float* bias, int act, float* y, cudaStream_t stream) {
+  const int Ht = 2 * Hin + 1, Wt = 2 * Win + 1;
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  if (static_cast<long long>(B) * C > 65535LL * 1) {
+    // grid.z limit is 65535
+    if (static_cast<long long>(B) * C > 65535) {
+      set_last_error("blur_up_act: B*C=%lld exceeds grid.z", static_cast<long long>(B) * C);
+      return RW_ERR_BAD_ARG;
+    }
+  }
+  dim3 grid((Wo + 31) / 32, (Ho + 7) / 8, B * C);
+  dim3 block(32, 8);
+  blur_up_act_kernel<<<grid, block, 0, stream>>>(t, C, Ht, Wt, kernel4x4, noise, noise_bstride,
+                                                 noise_w, bias, act, y);
+  return check_cuda(cudaGetLastError(), "blur_up_act launch");
+}
+
+int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
+                     int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
+                     int py1, float* out, int out_h, int out_w, cudaStream_t stream) {
+  (void)px1;
+  (void)py1;
+  const long long total = static_cast<long long>(major) * out_h * out_w;
+  if (total <= 0) return RW_OK;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  upfirdn2d_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      in, kernel, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, px0, py0, out, out_h, out_w,
+      total);
+  return check_cuda(cudaGetLastError(), "upfirdn2d launch");
+}
+
+int bias_act_launch(const float* x, const float* bias, const float* ref, int act, int grad,
+                    float alpha, float scale, long long n, int step_b, int size_b, float* y,
+                    cudaStream_t stream) {
+  if (n <= 0) return RW_OK;
+  bias_act_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, bias, ref, act, grad, alpha, scale, n,
+                                                        step_b > 0 ? step_b : 1,
+                                                        size_b > 0 ? size_b : 1, y);
+  return check_cuda(cudaGetLastError(), "bias_act launch");
+}
+
+int torgb_launch(const float* x, const float* style, const float* w, const float* bias,
+                 const float* skip, int B, int C, int H, int W, float scale, float* out,
+                 cudaStream_t stream) {
+  const int HW = H * W;
+  dim3 grid((HW + 255) / 256, B);
+  torgb_kernel<<<grid, 256, 3 * C * sizeof(float), stream>>>(x, style, w, bias, skip, C, HW, scale,
+                                                             out);
+  return check_cuda(cudaGetLastError(), "torgb launch");
+}
+
+int add_noise_launch(const float* x, const float* noise, long long noise_bstride, float noise_w,
+                     int B, int C, int HW, float* y, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (total <= 0) return RW_OK;
+  add_noise_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, noise, noise_bstride, noise_w, C,
+                                                             HW, total, y);
+  return check_cuda(cudaGetLastError(), "add_noise launch");
+}
+
+}  // namespace rw
