@@ -1,0 +1,27 @@
+"""rewriting_b200 — Blackwell-native hot path of davidbau/rewriting.
+
+Layout: `csrc/` (CUDA kernels + C-ABI, built into librw_b200.so), `ops` (torch-facing
+wrappers / autograd), `utils/` and `rewrite/` (host-side mirror of the reference's operator,
+module, statistics and rewriter APIs), `dist` (z-batch sharding).
+
+`install_aliases()` registers the package's `utils` and `rewrite` sub-packages under the
+reference's top-level import names so notebooks written against the reference
+(`from utils.stylegan2 import load_seq_stylegan`, `from rewrite import ganrewrite`) run
+unchanged.
+"""
+import sys
+
+__version__ = '0.1.0'
+
+
+def install_aliases():
+    from . import utils as _utils, rewrite as _rewrite
+    from .utils import nethook, pbar, renormalize, runningstats, tally, zdataset, stylegan2
+    from .rewrite import ganrewrite
+    sys.modules.setdefault('utils', _utils)
+    sys.modules.setdefault('rewrite', _rewrite)
+    for name, mod in [('nethook', nethook), ('pbar', pbar), ('renormalize', renormalize),
+                      ('runningstats', runningstats), ('tally', tally), ('zdataset', zdataset),
+                      ('stylegan2', stylegan2)]:
+        sys.modules.setdefault('utils.' + name, mod)
+    sys.modules.setdefault('rewrite.ganrewrite', ganrewrite)

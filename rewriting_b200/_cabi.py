@@ -103,8 +103,18 @@ def check(rc, what):
         raise RwError('%s failed (status %d): %s' % (what, rc, last_error()))
 
 
+# kernels launched per entry point (for bench.py's `gpu_launches` claim)
+LAUNCHES_PER_CALL = {
+    'rw_modconv_up_fwd': 4, 'rw_second_moment_accum': 2, 'rw_conv_wgrad': 2,
+    'rw_debug_colgemm': 2,
+}
+launch_count = 0
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and raise RwError on a non-zero status."""
+    global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
     check(rc, name)
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)

@@ -1,0 +1,410 @@
+"""Torch-facing wrappers over the C-ABI kernels (librw_b200.so).
+
+Every function here takes CUDA fp32 tensors, allocates outputs with torch (the
+library never allocates), and launches on torch's current stream.  Autograd is
+provided by explicit `torch.autograd.Function`s whose backward passes are the
+same tensor-core kernels run on gradient planes.
+
+Reference call sites replaced (davidbau/rewriting): utils/stylegan2/models.py
+313-329 (DemodulatedConv2dF), 535-546 (NoiseInjectionF), 616-626 (ApplyStyle,
+FusedLeakyReLUF), 628-655 (ToRGBF), op/fused_act.py, op/upfirdn2d.py,
+utils/runningstats.py:1086-1097, rewrite/ganrewrite.py:806-813.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    """contiguous fp32 CUDA view of t (the reference ops call .contiguous() too:
+    fused_bias_act_kernel.cu:58-60, upfirdn2d_kernel.cu:149-150)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _cabi.RwError('rewriting_b200 ops need CUDA tensors (got %s); there is no CPU '
+                            'fallback' % t.device)
+    if t.dtype != torch.float32:
+        raise _cabi.RwError('rewriting_b200 ops are fp32-in/fp32-out (got %s)' % t.dtype)
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- noise
+_NOISE_CACHE = {}
+
+
+def noise_table(batch, hw, device):
+    """The reference draws `np.random.RandomState(0).randn(batch, H*W)` on the host in
+    every NoiseInjectionF.forward (models.py:542-545).  The values only depend on
+    (batch, H*W); generate once and keep on the device."""
+    key = (batch, hw, str(device))
+    t = _NOISE_CACHE.get(key)
+    if t is None:
+        arr = np.random.RandomState(0).randn(batch, hw).astype('float32')
+        t = torch.from_numpy(arr).to(device)
+        if len(_NOISE_CACHE) > 64:
+            _NOISE_CACHE.clear()
+        _NOISE_CACHE[key] = t
+    return t
+
+
+# --------------------------------------------------------------------------- planes
+class KeyPlanes(object):
+    """bf16 hi/lo planes of a [B,C,H,W] tensor in the padded-flat channels-last layout."""
+    __slots__ = ('hi', 'lo', 'B', 'C', 'H', 'W')
+
+    def __init__(self, hi, lo, B, C, H, W):
+        self.hi, self.lo, self.B, self.C, self.H, self.W = hi, lo, B, C, H, W
+
+    @property
+    def rows(self):
+        return self.B * (self.H + 1) * (self.W + 1)
+
+
+def prep_keys(x, scale_bc=None, want_k=False):
+    """planes of (scale_bc[b,c] * x[b,c,y,x]); optionally also the fp32 NCHW product."""
+    x = _f32c(x)
+    scale_bc = _f32c(scale_bc)
+    B, C, H, W = x.shape
+    rows = B * (H + 1) * (W + 1)
+    hi = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    k = torch.empty_like(x) if want_k else None
+    _cabi.call('rw_prep_keys', _p(x), _p(scale_bc), B, C, H, W, _p(hi), _p(lo), _p(k), _stream())
+    return KeyPlanes(hi, lo, B, C, H, W), k
+
+
+def split_rows(a):
+    a = _f32c(a)
+    hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    lo = torch.empty_like(hi)
+    _cabi.call('rw_split_rows', _p(a), a.numel(), _p(hi), _p(lo), _stream())
+    return hi, lo
+
+
+_WEIGHT_CACHE = {}
+
+
+def weight_planes(weight, kind='fwd'):
+    """(hi, lo, wsq) planes of scale*W for a [1,Cout,Cin,3,3] / [Cout,Cin,3,3] tensor.
+    Cached per tensor OBJECT (weak reference) and `_version`: the rewriter mutates W in
+    place, which bumps `_version` and invalidates the entry; temporaries
+    (e.g. linear_insert's W0 + Lambda d) are new objects and never hit a stale entry."""
+    import weakref
+    w = weight.detach()
+    if w.dim() == 5:
+        w = w[0]
+    Cout, Cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    key = (id(weight), kind)
+    ent = _WEIGHT_CACHE.get(key)
+    if ent is not None and ent[0]() is weight and ent[1] == weight._version:
+        return ent[2]
+    w = _f32c(w)
+    scale = 1.0 / math.sqrt(Cin * 9)
+    hi = torch.empty((Cout * 9 * Cin,), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi)
+    if kind == 'fwd':
+        wsq = torch.empty((Cout, Cin), dtype=torch.float32, device=w.device)
+        _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 0, 0, _p(hi), _p(lo), _p(wsq),
+                   _stream())
+    elif kind == 'dgrad':      # [Cin][flipped tap][Cout]
+        wsq = None
+        _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 1, 1, _p(hi), _p(lo), None,
+                   _stream())
+    else:
+        raise ValueError(kind)
+    val = (hi, lo, wsq)
+    if isinstance(weight, torch.nn.Parameter):
+        if len(_WEIGHT_CACHE) > 256:
+            _WEIGHT_CACHE.clear()
+        _WEIGHT_CACHE[key] = (weakref.ref(weight), weight._version, val)
+    return val
+
+
+def demod_factors(style, wsq, eps=1e-8):
+    style = _f32c(style)
+    B, Cin = style.shape
+    Cout = wsq.shape[0]
+    out = torch.empty((B, Cout), dtype=torch.float32, device=style.device)
+    _cabi.call('rw_demod', _p(style), _p(wsq), B, Cout, Cin, eps, _p(out), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- conv kernels
+def conv3x3_planes(planes, w_hi, w_lo, Cout, scale_bo=None, noise=None, noise_w=0.0, bias=None,
+                   act=False):
+    """row-GEMM 3x3 conv (pad 1) over key planes -> [B,Cout,H,W] fp32."""
+    B, Cin, H, W = planes.B, planes.C, planes.H, planes.W
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=planes.hi.device)
+    nstride = noise.stride(0) if noise is not None else 0
+    _cabi.call('rw_modconv_fwd', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo), _p(scale_bo),
+               _p(noise), nstride, float(noise_w), _p(bias), 1 if act else 0, B, Cin, Cout, H, W,
+               _p(out), _stream())
+    return out
+
+
+def convT3x3_planes(planes, w_hi, w_lo, Cout, scale_bo=None):
+    """conv_transpose2d(stride 2, pad 0) over key planes -> [B,Cout,2H+1,2W+1] fp32."""
+    B, Cin, H, W = planes.B, planes.C, planes.H, planes.W
+    out = torch.empty((B, Cout, 2 * H + 1, 2 * W + 1), dtype=torch.float32,
+                      device=planes.hi.device)
+    _cabi.call('rw_modconv_up_fwd', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
+               _p(scale_bo), B, Cin, Cout, H, W, _p(out), _stream())
+    return out
+
+
+def blur_up_act(t, kernel, noise=None, noise_w=0.0, bias=None, act=False):
+    t = _f32c(t)
+    B, C, Ht, Wt = t.shape
+    Hin, Win = (Ht - 1) // 2, (Wt - 1) // 2
+    y = torch.empty((B, C, 2 * Hin, 2 * Win), dtype=torch.float32, device=t.device)
+    nstride = noise.stride(0) if noise is not None else 0
+    _cabi.call('rw_blur_up_act', _p(t), B, C, Hin, Win, _p(_f32c(kernel)), _p(noise), nstride,
+               float(noise_w), _p(bias), 1 if act else 0, _p(y), _stream())
+    return y
+
+
+def add_noise(x, noise, noise_w):
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    _cabi.call('rw_add_noise', _p(x), _p(noise), noise.stride(0), float(noise_w), B, C, H * W,
+               _p(y), _stream())
+    return y
+
+
+def torgb(x, style, weight, bias, skip=None):
+    """out = conv1x1(style*x, W/sqrt(C)) + bias (+ skip)   (ToRGBF, models.py:639-655)."""
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    _cabi.call('rw_torgb', _p(x), _p(_f32c(style)), _p(_f32c(weight.reshape(3, C))),
+               _p(_f32c(bias.reshape(3))), _p(_f32c(skip)), B, C, H, W, 1.0 / math.sqrt(C),
+               _p(out), _stream())
+    return out
+
+
+def fused_bias_act_raw(x, bias, ref, act, grad, alpha, scale):
+    """The reference's `fused.fused_bias_act` (op/fused_bias_act.cpp:11-21)."""
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    has_b = bias is not None and bias.numel() > 0
+    has_r = ref is not None and ref.numel() > 0
+    step_b = 1
+    for i in range(2, x.dim()):
+        step_b *= x.shape[i]
+    _cabi.call('rw_fused_bias_act', _p(x), _p(_f32c(bias)) if has_b else None,
+               _p(_f32c(ref)) if has_r else None, int(act), int(grad), float(alpha), float(scale),
+               x.numel(), step_b, bias.numel() if has_b else 1, _p(y), _stream())
+    return y
+
+
+def upfirdn2d_raw(inp, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    """The reference's `upfirdn2d_op.upfirdn2d` on a [major, H, W, 1] view
+    (op/upfirdn2d.cpp:4-22)."""
+    inp = _f32c(inp)
+    major, in_h, in_w, minor = inp.shape
+    if minor != 1:
+        inp = inp.permute(0, 3, 1, 2).contiguous()
+        major_eff = major * minor
+    else:
+        major_eff = major
+    kh, kw = kernel.shape
+    out_h = (in_h * up_y + py0 + py1 - kh) // down_y + 1
+    out_w = (in_w * up_x + px0 + px1 - kw) // down_x + 1
+    out = torch.empty((major_eff, out_h, out_w), dtype=torch.float32, device=inp.device)
+    _cabi.call('rw_upfirdn2d', _p(inp), _p(_f32c(kernel)), major_eff, in_h, in_w, kh, kw, up_x,
+               up_y, down_x, down_y, px0, px1, py0, py1, _p(out), out_h, out_w, _stream())
+    if minor != 1:
+        return out.view(major, minor, out_h, out_w).permute(0, 2, 3, 1).contiguous()
+    return out.view(major, out_h, out_w, 1)
+
+
+# --------------------------------------------------------------------------- second moment
+_WS = {}
+
+
+def _workspace(nbytes, device):
+    key = str(device)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((nbytes + 3) // 4 + 64, dtype=torch.float32, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def second_moment_accum_planes(mom2, hi, lo):
+    """mom2 += hi/lo planes^T @ planes  (RunningSecondMoment.add, runningstats.py:1086-1097)."""
+    rows, C = hi.shape
+    lib = _cabi.load()
+    ws = _workspace(lib.rw_gram_workspace_bytes(C, C, rows, 1), hi.device)
+    _cabi.call('rw_second_moment_accum', _p(hi), _p(lo), rows, C, _p(mom2), _p(ws),
+               ws.numel() * 4, _stream())
+
+
+def second_moment_accum(mom2, a):
+    hi, lo = split_rows(a)
+    second_moment_accum_planes(mom2, hi, lo)
+
+
+def conv_wgrad_planes(g_planes, k_planes):
+    """dWt[o][tap][i] = sum_p G[p,o] K[p+shift(tap), i]  -> [Cout, 9, Cin] fp32."""
+    rows = g_planes.rows
+    Cout, Cin = g_planes.C, k_planes.C
+    lib = _cabi.load()
+    ws = _workspace(lib.rw_gram_workspace_bytes(Cout, Cin, rows, 9), g_planes.hi.device)
+    out = torch.empty((Cout, 9, Cin), dtype=torch.float32, device=g_planes.hi.device)
+    _cabi.call('rw_conv_wgrad', _p(g_planes.hi), _p(g_planes.lo), _p(k_planes.hi),
+               _p(k_planes.lo), rows, Cout, Cin, k_planes.W + 1, _p(out), _p(ws), ws.numel() * 4,
+               _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- rank projection
+def project_rank(weight, direction, base=None, sign=1.0):
+    """base + sign * projected_conv(weight, direction)   (ganrewrite.py:806-813)."""
+    w = _f32c(weight)
+    d = _f32c(direction)
+    shp = w.shape
+    if w.dim() == 5:
+        Cout, Cin, taps = shp[1], shp[2], shp[3] * shp[4]
+        assert shp[0] == 1
+    else:
+        Cout, Cin, taps = shp[0], shp[1], shp[2] * shp[3]
+    rank = d.shape[0]
+    out = torch.empty_like(w)
+    _cabi.call('rw_project_rank', _p(w), _p(_f32c(base)), _p(d), rank, Cout, Cin, taps,
+               float(sign), _p(out), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- autograd
+LRELU_SLOPE = 0.2
+LRELU_GAIN = 2 ** 0.5
+
+
+class StyledConvFunction(torch.autograd.Function):
+    """y = [act]([blur](conv(style*x, scale*W) * demod) + nw*noise + bias)
+
+    One fused forward (prep -> tcgen05 row-GEMM with fused epilogue); backward =
+    dgrad row-GEMM on gradient planes + wgrad col-GEMM + small reductions.
+    """
+
+    @staticmethod
+    def forward(ctx, x, style, weight, noise_weight, bias, upsample, blur_kernel, demodulate,
+                with_noise, with_act, pre_modulated, wholder):
+        x = _f32c(x)
+        style = _f32c(style)
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[-4]
+        if pre_modulated:
+            planes, _ = prep_keys(x, None)
+        else:
+            planes, _ = prep_keys(x, style)
+        w_hi, w_lo, wsq = wholder.planes('fwd')
+        dm = demod_factors(style, wsq) if demodulate else None
+        nw = float(noise_weight.detach().item()) if (with_noise and noise_weight is not None) else 0.0
+        b = _f32c(bias.detach()) if (with_act and bias is not None) else None
+        if upsample:
+            t = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)
+            Ho, Wo = 2 * H, 2 * W
+            noise = noise_table(B, Ho * Wo, x.device) if with_noise else None
+            y = blur_up_act(t, blur_kernel, noise, nw, b, with_act)
+        else:
+            noise = noise_table(B, H * W, x.device) if with_noise else None
+            y = conv3x3_planes(planes, w_hi, w_lo, Cout, dm, noise, nw, b, with_act)
+        ctx.save_for_backward(x, style, weight, noise_weight, bias, y, dm)
+        ctx.cfg = (upsample, demodulate, with_noise, with_act, pre_modulated)
+        ctx.blur_kernel = blur_kernel
+        ctx.wholder = wholder
+        ctx.planes = planes if not upsample else None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, style, weight, noise_weight, bias, y, dm = ctx.saved_tensors
+        upsample, demodulate, with_noise, with_act, pre_modulated = ctx.cfg
+        if upsample:
+            raise _cabi.RwError('StyledConvFunction.backward: upsample layers are forward-only in '
+                                'this round (use an even target layer)')
+        gy = _f32c(gy)
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[-4]
+        sc = 1.0 / math.sqrt(Cin * 9)
+        w4 = weight.detach().reshape(Cout, Cin, 3, 3)
+        # through the activation: gate on the sign of the saved output
+        if with_act:
+            g_pre = fused_bias_act_raw(gy, None, y, 3, 1, LRELU_SLOPE, LRELU_GAIN)
+        else:
+            g_pre = gy
+        g_bias = g_pre.sum(dim=(0, 2, 3)) if (with_act and bias is not None) else None
+        g_nw = None
+        noise = noise_table(B, H * W, x.device) if with_noise else None
+        if with_noise and noise_weight is not None:
+            g_nw = (g_pre.sum(dim=1).reshape(B, -1) * noise).sum().reshape(1)
+        # gradient planes of g_t = g_pre * demod
+        g_planes, _ = prep_keys(g_pre, dm)
+        # dgrad: dk = conv(g_t, flip(W)^T)
+        wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad')
+        dk = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)
+        if pre_modulated:
+            gx, g_style = dk, None
+            k_planes = ctx.planes
+        else:
+            gx = dk * style[:, :, None, None]
+            g_style = (dk * x).sum(dim=(2, 3))
+            k_planes = ctx.planes
+        # wgrad
+        dwt = conv_wgrad_planes(g_planes, k_planes)            # [Cout, 9, Cin]
+        gW = (sc * dwt).permute(0, 2, 1).reshape(Cout, Cin, 3, 3)
+        if demodulate:
+            # recover t*demod = pre-activation - noise - bias from the saved output
+            if with_act:
+                pre = torch.where(y > 0, y / LRELU_GAIN, y / (LRELU_SLOPE * LRELU_GAIN))
+                if bias is not None:
+                    pre = pre - bias.detach().view(1, -1, 1, 1)
+            else:
+                pre = y
+            if with_noise and noise_weight is not None:
+                pre = pre - noise_weight.detach() * noise.view(B, 1, H, W)
+            Gd = (g_pre * pre).sum(dim=(2, 3))                 # = dL/d(demod) * demod
+            coef = Gd * dm * dm                                # dL/ddemod * demod^3 / demod ...
+            s2 = style * style
+            # d demod/dW = -demod^3 * sc^2 * W * s^2 ;  dL/ddemod = Gd/demod
+            gW = gW - (sc * sc) * w4 * torch.matmul(coef.t(), s2)[:, :, None, None]
+            if g_style is not None:
+                wsq = ctx.wholder.planes('fwd')[2]
+                g_style = g_style - style * torch.matmul(coef, wsq)
+        gW = gW.reshape(weight.shape)
+        return gx, g_style, gW, g_nw, g_bias, None, None, None, None, None, None, None
+
+
+class _WeightHolder(object):
+    """Carries the caller's weight OBJECT into the autograd Function so that the plane cache
+    is keyed on the user's Parameter, not on whatever view autograd hands to forward()."""
+    __slots__ = ('weight',)
+
+    def __init__(self, weight):
+        self.weight = weight
+
+    def planes(self, kind):
+        return weight_planes(self.weight, kind)
+
+
+def styled_conv(x, style, weight, noise_weight=None, bias=None, upsample=False, blur_kernel=None,
+                demodulate=True, with_noise=True, with_act=True, pre_modulated=False):
+    return StyledConvFunction.apply(x, style, weight, noise_weight, bias, upsample, blur_kernel,
+                                    demodulate, with_noise, with_act, pre_modulated,
+                                    _WeightHolder(weight))

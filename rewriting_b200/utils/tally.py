@@ -1,0 +1,106 @@
+"""Batched statistic drivers with .npz caching (API of the reference's `utils/tally.py`,
+hot-path subset): `tally_second_moment`, `tally_mean`, `make_loader`,
+`load_cached_state`, `save_cached_state`.
+
+`tally_second_moment(compute, dataset, sample_size=None, batch_size=10, cachefile=None)`
+(reference: tally.py:424-443) iterates a DataLoader over the z dataset, calls
+`compute(zbatch)` -> [N, C] samples and adds them to a `RunningSecondMoment`.  Cache files
+are `numpy.savez(cachefile, **state_dict, **args)` and are validated against `args` on load
+(tally.py:703-730) — same keys/dtypes as the reference so caches interchange.
+
+Extension (not in the reference): `compute` may return `ops.KeyPlanes` instead of a tensor,
+in which case the planes feed the tensor-core accumulator directly with no fp32 round trip
+(used by the rewriter's fused key capture).
+"""
+import os
+
+import numpy
+import torch
+import torch.utils.data
+
+from . import pbar, runningstats
+from .sampler import FixedSubsetSampler
+from .. import ops
+
+
+def call_compute(compute, batch):
+    if isinstance(batch, list):
+        return compute(*batch)
+    if isinstance(batch, dict):
+        return compute(**batch)
+    return compute(batch)
+
+
+def make_loader(dataset, sample_size=None, batch_size=10, sampler=None, **kwargs):
+    """DataLoader over a fixed prefix of `dataset` (a tensor is wrapped in a TensorDataset)."""
+    if isinstance(dataset, torch.Tensor):
+        dataset = torch.utils.data.TensorDataset(dataset)
+    if sampler is None and sample_size is not None:
+        if sample_size > len(dataset):
+            pbar.print('Warning: sample size %d > dataset size %d' % (sample_size, len(dataset)))
+            sample_size = len(dataset)
+        sampler = FixedSubsetSampler(list(range(sample_size)))
+    return torch.utils.data.DataLoader(dataset, sampler=sampler, batch_size=batch_size, **kwargs)
+
+
+def load_cached_state(cachefile, args):
+    if cachefile is None:
+        return None
+    try:
+        dat = numpy.load(cachefile, allow_pickle=True)
+        for a, v in args.items():
+            if a not in dat or dat[a] != v:
+                pbar.print('%s %s changed from %s to %s' % (cachefile, a, dat[a], v))
+                return None
+    except Exception:
+        return None
+    pbar.descnext(None)
+    pbar.print('Loading cached %s' % cachefile)
+    return dat
+
+
+def save_cached_state(cachefile, obj, args):
+    if cachefile is None:
+        return
+    dirname = os.path.dirname(cachefile)
+    if dirname:
+        os.makedirs(dirname, exist_ok=True)
+    dat = obj.state_dict()
+    for a, v in args.items():
+        if a in dat:
+            assert dat[a] == v
+        dat[a] = v
+    numpy.savez(cachefile, **dat)
+
+
+def tally_second_moment(compute, dataset, sample_size=None, batch_size=10, cachefile=None,
+                        **kwargs):
+    args = dict(sample_size=sample_size)
+    cached = load_cached_state(cachefile, args)
+    if cached is not None:
+        return runningstats.RunningSecondMoment(state=cached)
+    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    r2mom = runningstats.RunningSecondMoment()
+    for batch in pbar(loader):
+        sample = call_compute(compute, batch)
+        if isinstance(sample, ops.KeyPlanes):
+            r2mom.add_planes(sample.hi, sample.lo, sample.B * sample.H * sample.W)
+        else:
+            r2mom.add(sample)
+    r2mom.to_('cpu')
+    save_cached_state(cachefile, r2mom, args)
+    return r2mom
+
+
+def tally_mean(compute, dataset, sample_size=None, batch_size=10, cachefile=None, **kwargs):
+    args = dict(sample_size=sample_size)
+    cached = load_cached_state(cachefile, args)
+    if cached is not None:
+        return runningstats.RunningMean(state=cached)
+    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    rmean = runningstats.RunningMean()
+    for batch in pbar(loader):
+        rmean.add(call_compute(compute, batch))
+    rmean.to_('cpu')
+    save_cached_state(cachefile, rmean, args)
+    return rmean

@@ -1,0 +1,310 @@
+"""GPU (B200): the CUDA path against the CPU oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): pixels within 1e-3 fp32 on identical z/seed, edited W
+within 1e-4 (over <= 50 iterations), C rel-Frobenius <= 1e-5, d max-abs <= 1e-4.
+Conv operands are 3-term split bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sg2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cuda_model(seeded_model):
+    import copy
+    return copy.deepcopy(seeded_model).cuda().eval()
+
+
+# ------------------------------------------------------------------------------------------
+# kernel level
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('B,C,H,W', [(2, 64, 4, 4), (3, 128, 5, 7), (1, 512, 32, 32), (2, 128, 40, 33)])
+def test_prep_keys_layout_and_split(B, C, H, W):
+    from rewriting_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, device='cuda')
+    s = torch.randn(B, C, device='cuda')
+    planes, k = ops.prep_keys(x, s, want_k=True)
+    k_ref = s[:, :, None, None] * x
+    assert torch.equal(k, k_ref)                                  # fp32 product, same rounding
+    hi = planes.hi.float().view(B, H + 1, W + 1, C)
+    lo = planes.lo.float().view(B, H + 1, W + 1, C)
+    assert hi[:, H].abs().max() == 0 and hi[:, :, W].abs().max() == 0    # zero pad row / col
+    assert lo[:, H].abs().max() == 0 and lo[:, :, W].abs().max() == 0
+    rec = (hi + lo)[:, :H, :W].permute(0, 3, 1, 2)
+    err = (rec - k_ref).abs().max().item()
+    assert err <= 2 ** -16 * k_ref.abs().max().item()
+    assert torch.equal(planes.hi.view(B, H + 1, W + 1, C)[:, :H, :W].permute(0, 3, 1, 2),
+                       k_ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,W,act', [
+    (2, 128, 128, 8, 8, True), (3, 64, 256, 5, 9, False), (1, 512, 512, 32, 32, True),
+    (8, 512, 512, 4, 4, True), (2, 256, 128, 19, 33, True)])
+def test_styled_conv_forward_vs_oracle(B, Cin, Cout, H, W, act):
+    from rewriting_b200 import ops
+    torch.manual_seed(1)
+    x = torch.randn(B, Cin, H, W)
+    style = torch.randn(B, Cin) * 0.5 + 1.0
+    weight = torch.randn(1, Cout, Cin, 3, 3)
+    nw = torch.tensor([0.37])
+    bias = torch.randn(Cout)
+    k = style[:, :, None, None] * x
+    if act:
+        ref = orc.target_forward(k, style, weight, nw, bias, True)
+    else:
+        ref = orc.demod_conv(k, style, weight, upsample=False)
+    wp = torch.nn.Parameter(weight.cuda())
+    with torch.no_grad():
+        y = ops.styled_conv(x.cuda(), style.cuda(), wp, torch.nn.Parameter(nw.cuda()),
+                            torch.nn.Parameter(bias.cuda()), upsample=False, demodulate=True,
+                            with_noise=act, with_act=act)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,W', [(2, 128, 128, 4, 4), (1, 512, 256, 16, 16),
+                                             (3, 64, 128, 7, 5)])
+def test_styled_conv_upsample_vs_oracle(B, Cin, Cout, H, W):
+    from rewriting_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(B, Cin, H, W)
+    style = torch.randn(B, Cin) * 0.5 + 1.0
+    weight = torch.randn(1, Cout, Cin, 3, 3)
+    nw, bias = torch.tensor([0.37]), torch.randn(Cout)
+    k = style[:, :, None, None] * x
+    t = orc.demod_conv(k, style, weight, upsample=True)
+    kern = orc.make_kernel([1, 3, 3, 1]) * 4
+    tb = orc.upfirdn2d(t, kern, pad=(1, 1))
+    n = orc.noise_table(B, 4 * H * W).view(B, 1, 2 * H, 2 * W)
+    ref = orc.fused_leaky_relu(tb + nw * n, bias)
+    with torch.no_grad():
+        y = ops.styled_conv(x.cuda(), style.cuda(), torch.nn.Parameter(weight.cuda()),
+                            torch.nn.Parameter(nw.cuda()), torch.nn.Parameter(bias.cuda()),
+                            upsample=True, blur_kernel=kern.cuda(), demodulate=True)
+    assert y.shape == ref.shape
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def test_styled_conv_backward_vs_oracle_autograd():
+    from rewriting_b200 import ops
+    torch.manual_seed(3)
+    B, Cin, Cout, H, W = 2, 128, 128, 6, 7
+    x = torch.randn(B, Cin, H, W, requires_grad=True)
+    style = (torch.randn(B, Cin) * 0.5 + 1.0).requires_grad_(True)
+    weight = torch.randn(1, Cout, Cin, 3, 3, requires_grad=True)
+    nw = torch.tensor([0.37], requires_grad=True)
+    bias = torch.randn(Cout, requires_grad=True)
+    gy = torch.randn(B, Cout, H, W)
+    ref = orc.target_forward(style[:, :, None, None] * x, style, weight, nw, bias, True)
+    ref.backward(gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    sc = style.detach().cuda().requires_grad_(True)
+    wc = torch.nn.Parameter(weight.detach().cuda())
+    nc = torch.nn.Parameter(nw.detach().cuda())
+    bc = torch.nn.Parameter(bias.detach().cuda())
+    y = ops.styled_conv(xc, sc, wc, nc, bc, upsample=False, demodulate=True)
+    y.backward(gy.cuda())
+    for name, got, want in [('x', xc.grad, x.grad), ('style', sc.grad, style.grad),
+                            ('weight', wc.grad, weight.grad), ('noise_w', nc.grad, nw.grad),
+                            ('bias', bc.grad, bias.grad)]:
+        err = (got.cpu() - want).abs().max().item()
+        assert err < 3e-4 * max(1.0, want.abs().max().item()), (name, err)
+
+
+def test_operator_level_ops_vs_oracle():
+    from rewriting_b200.utils.stylegan2 import op
+    torch.manual_seed(4)
+    x = torch.randn(3, 16, 9, 11)
+    b = torch.randn(16)
+    y = op.fused_leaky_relu(x.cuda(), b.cuda())
+    assert torch.allclose(y.cpu(), orc.fused_leaky_relu(x, b), atol=1e-6)
+    lin = torch.randn(5, 16)
+    assert torch.allclose(op.fused_leaky_relu(lin.cuda(), b.cuda()).cpu(),
+                          orc.fused_leaky_relu(lin, b), atol=1e-6)
+    # backward gates on the saved output
+    xc = x.cuda().requires_grad_(True)
+    bc = b.cuda().requires_grad_(True)
+    op.fused_leaky_relu(xc, bc).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    orc.fused_leaky_relu(xr, br).sum().backward()
+    assert torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-6)
+    assert torch.allclose(bc.grad.cpu(), br.grad, atol=1e-4)
+    k = orc.make_kernel([1, 3, 3, 1])
+    for up, down, pad in [(2, 1, (2, 1)), (1, 1, (1, 1)), (1, 2, (1, 1)), (1, 1, (2, 2)),
+                          (2, 1, (-1, 2))]:
+        kk = k * (up * up)
+        ref = orc.upfirdn2d(x, kk, up=up, down=down, pad=pad)
+        got = op.upfirdn2d(x.cuda(), kk.cuda(), up=up, down=down, pad=pad)
+        assert got.shape == ref.shape, (up, down, pad)
+        assert torch.allclose(got.cpu(), ref, atol=1e-5), (up, down, pad)
+    xg = x.cuda().requires_grad_(True)
+    op.upfirdn2d(xg, (k * 4).cuda(), up=2, pad=(2, 1)).pow(2).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    orc.upfirdn2d(xr, k * 4, up=2, pad=(2, 1)).pow(2).sum().backward()
+    assert torch.allclose(xg.grad.cpu(), xr.grad, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        op.fused_leaky_relu(x, b)            # CPU tensors are rejected like the reference
+
+
+def test_second_moment_kernel_vs_oracle():
+    from rewriting_b200.utils import runningstats
+    torch.manual_seed(5)
+    r = runningstats.RunningSecondMoment()
+    mom_ref = torch.zeros(512, 512, dtype=torch.float64)
+    total = 0
+    for n in (10240, 37, 64, 5000):                 # ragged batch sizes
+        a = torch.randn(n, 512) * torch.linspace(0.1, 3, 512)
+        r.add(a.cuda())
+        mom_ref += a.double().t() @ a.double()
+        total += n
+    r.add(torch.zeros(0, 512).cuda())               # empty batch
+    assert r.count == total
+    got = r.mom2.double().cpu()
+    rel = ((got - mom_ref).norm() / mom_ref.norm()).item()
+    assert rel < 1e-5, rel
+    assert torch.equal(r.mom2, r.mom2.t())           # exactly symmetric (mirrored upper triangle)
+    # linearity: accumulating a twice equals 2x
+    r2 = runningstats.RunningSecondMoment()
+    a = torch.randn(4096, 128).cuda()
+    r2.add(a)
+    once = r2.mom2.clone()
+    r2.add(a)
+    assert torch.allclose(r2.mom2, 2 * once, rtol=1e-6, atol=1e-3)
+
+
+def test_projected_conv_vs_oracle():
+    from rewriting_b200.rewrite import ganrewrite
+    torch.manual_seed(6)
+    W = torch.randn(1, 512, 512, 3, 3)
+    q, _ = torch.linalg.qr(torch.randn(512, 3))
+    d = q.t().contiguous()
+    ref = orc.projected_conv(W, d)
+    got = ganrewrite.projected_conv(W.cuda(), d.cuda())
+    assert torch.allclose(got.cpu(), ref, atol=2e-5)
+    ortho = ganrewrite.projected_conv(W.cuda(), d.cuda(), base=W.cuda(), sign=-1.0)
+    assert torch.allclose(ortho.cpu(), W - ref, atol=2e-5)
+    assert torch.allclose(ganrewrite.projected_conv(W[0].cuda(), d.cuda()).cpu(), ref[0], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# model level
+# ------------------------------------------------------------------------------------------
+def test_generator_pixels_vs_golden_and_oracle(cuda_model, seeded_sd, z40, golden):
+    with torch.no_grad():
+        pix = cuda_model(z40[:2].cuda()).cpu()
+    assert pix.shape == (2, 3, 256, 256)
+    err_g = np.abs(pix[:, :, ::8, ::8].numpy() - golden['pixels_sub']).max()
+    assert err_g < 1e-3, err_g                       # north_star: pixels within 1e-3
+    with torch.no_grad():
+        ref = orc.generator_forward(seeded_sd, z40[:2])
+    err = (pix - ref).abs().max().item()
+    assert err < 1e-3, err
+    # batch-size independence of the fused path (noise depends only on (i, H*W))
+    with torch.no_grad():
+        one = cuda_model(z40[1:2].cuda()).cpu()
+    assert (one[0] - pix[1]).abs().max().item() < 1e-3
+
+
+def test_fused_layers_equal_leaf_by_leaf_execution(cuda_model, z40):
+    """The nethook-split execution (context | target | rendering, leaves one by one) must give
+    the same image as the fused whole-layer path."""
+    from rewriting_b200.utils import nethook
+    first, last = 'layer8.sconv.mconv.dconv', 'layer8.sconv.activate'
+    ctx = nethook.subsequence(cuda_model, upto_layer=first, share_weights=True)
+    tgt = nethook.subsequence(cuda_model, first_layer=first, last_layer=last, share_weights=True)
+    rnd = nethook.subsequence(cuda_model, after_layer=last, share_weights=True)
+    z = z40[:3].cuda()
+    with torch.no_grad():
+        whole = cuda_model(z)
+        split = rnd(tgt(ctx(z)))
+    assert (whole - split).abs().max().item() < 2e-4
+    # hooks force the per-child path and still see the layer output
+    with nethook.InstrumentedModel(cuda_model) as inst, torch.no_grad():
+        inst.retain_layer('layer8.sconv.mconv.adain', detach=False)
+        hooked = inst(z)
+        key = inst.retained_layer('layer8.sconv.mconv.adain')
+    assert key.fmap.shape == (3, 512, 32, 32)
+    assert (hooked - whole).abs().max().item() < 2e-4
+    assert torch.allclose(key.fmap, ctx(z).fmap, atol=1e-5)
+
+
+def test_rewriter_statistics_direction_and_edit_vs_golden(cuda_model, z40, golden, edit_request,
+                                                          seeded_sd):
+    from rewriting_b200.rewrite import ganrewrite
+    zds = torch.utils.data.TensorDataset(z40)
+    gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8)
+    assert tuple(gw.k_shape) == (1, 512, 32, 32) and tuple(gw.v_shape) == (1, 512, 32, 32)
+    C = gw.c_matrix.cpu()
+    sub_err = np.abs(C[::8, ::8].numpy() - golden['C_sub']).max()
+    assert sub_err < 2e-5 * float(golden['C_diag'].max()), sub_err
+    assert abs(float(C.trace()) - float(golden['C_trace'])) < 1e-5 * float(golden['C_trace'])
+    np.testing.assert_allclose(C.diag().numpy(), golden['C_diag'], rtol=2e-5)
+    # direction
+    d = gw.multi_key_from_selection(edit_request['key'], rank=1).cpu()
+    assert (d - torch.from_numpy(golden['d'])).abs().max().item() < 1e-4
+    # goal crops
+    obj_acts, _, obj_area, ob = gw.object_from_selection(*edit_request['object'])
+    goal_in, goal_out, _, pb = gw.paste_from_selection(edit_request['paste'][0],
+                                                       edit_request['paste'][1], obj_acts, obj_area)
+    assert tuple(ob) == tuple(golden['obj_bounds']) and tuple(pb) == tuple(golden['paste_bounds'])
+    assert (goal_in.fmap.cpu() - torch.from_numpy(golden['goal_in_fmap'])).abs().max() < 2e-4
+    assert (goal_out.fmap.cpu() - torch.from_numpy(golden['goal_out_fmap'])).abs().max() < 2e-4
+    # the edit: identical state and direction as the reference run, 11 iterations
+    gin = type(goal_in)(goal_in, fmap=torch.from_numpy(golden['goal_in_fmap']).cuda(),
+                        style=torch.from_numpy(golden['goal_in_style']).cuda())
+    gout = type(goal_out)(goal_out, fmap=torch.from_numpy(golden['goal_out_fmap']).cuda())
+    W0 = gw.target_weights().detach().clone()
+    losses = []
+    gw.insert(gin, gout, torch.from_numpy(golden['d']).cuda(), niter=int(golden['niter']),
+              piter=10, lr=0.05, update_callback=lambda it, loss: losses.append(float(loss)))
+    W = gw.target_weights().detach()
+    delta = (W - W0).cpu()
+    err = np.abs(delta[0, ::37, ::41].numpy() - golden['W_delta_sub']).max()
+    assert err < 1e-4, err                                    # edited W within 1e-4
+    assert abs(float(delta.norm()) - float(golden['W_delta_fro'])) < 1e-3 * float(golden['W_delta_fro'])
+    np.testing.assert_allclose(np.array(losses), golden['losses'], rtol=2e-4)
+    s = torch.linalg.svdvals(delta[0].permute(0, 2, 3, 1).reshape(-1, 512).double())
+    assert float(s[1] / s[0]) < 1e-5                           # rank one, as the paper requires
+    # the edit is visible to the full model (shared parameters) and to a re-render
+    assert gw.model.layer8.sconv.mconv.dconv.weight is gw.target_weights()
+    with torch.no_grad():
+        img = gw.sample_image_from_latent(z40[7:8].cuda())
+    assert torch.isfinite(img).all()
+
+
+def test_fused_insert_equals_autograd_insert_and_oracle(cuda_model, z40, golden):
+    """Same state, same d: fused one-kernel loop == autograd loop on the conv kernels == CPU
+    oracle, over 30 iterations (short horizon)."""
+    from rewriting_b200.rewrite import ganrewrite
+    zds = torch.utils.data.TensorDataset(z40[:10])
+    results = {}
+    for mode in ('fused', 'autograd'):
+        gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8, fused_insert=(mode == 'fused'))
+        bag = gw.context_model(gw.get_z(0))
+        gin = type(bag)(bag, fmap=torch.from_numpy(golden['goal_in_fmap']).cuda(),
+                        style=torch.from_numpy(golden['goal_in_style']).cuda())
+        gout = type(bag)(bag, fmap=torch.from_numpy(golden['goal_out_fmap']).cuda())
+        W0 = gw.target_weights().detach().clone().cpu()
+        gw.insert(gin, gout, torch.from_numpy(golden['d']).cuda(), niter=30, piter=10, lr=0.05)
+        results[mode] = gw.target_weights().detach().cpu()
+    sd = cuda_model.state_dict()
+    W_orc = orc.insert_loop(W0, torch.from_numpy(golden['goal_in_fmap']),
+                            torch.from_numpy(golden['goal_in_style']),
+                            torch.from_numpy(golden['goal_out_fmap']),
+                            sd['layer8.sconv.noise.weight'].cpu(),
+                            sd['layer8.sconv.activate.bias'].cpu(),
+                            torch.from_numpy(golden['d']), 30, piter=10, lr=0.05)
+    assert (results['fused'] - W_orc).abs().max().item() < 1e-4
+    assert (results['autograd'] - W_orc).abs().max().item() < 1e-4
+    assert (results['fused'] - results['autograd']).abs().max().item() < 1e-4
+    assert (W_orc - W0).abs().max().item() > 0.05             # the loop really moved W

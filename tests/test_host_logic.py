@@ -1,0 +1,198 @@
+"""CPU: host-side mirror of the reference API — module tree, nethook surgery, DataBag, z
+sampling, mask decoding, cache format, paste/crop helpers, and that the C-ABI library loads
+and exports every declared symbol (no kernels are launched here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from rewriting_b200 import _cabi
+from rewriting_b200.utils import nethook, renormalize, runningstats, tally, zdataset
+from rewriting_b200.utils.stylegan2 import models as sg2
+from rewriting_b200.rewrite import ganrewrite
+from conftest import ROOT
+
+
+def test_cabi_loads_and_exports_every_declared_symbol():
+    lib = _cabi.load()
+    assert lib.rw_version() >= 100
+    header = open(os.path.join(ROOT, 'include', 'rewriting_b200.h')).read()
+    body = header[header.index('extern "C"'):]
+    declared = set(re.findall(r'^(?:int|size_t|const char\*)\s+(rw_[a-z0-9_]+)\s*\(', body, re.M))
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'missing export ' + name
+        assert name in _cabi.SIGNATURES, 'no ctypes prototype for ' + name
+    assert lib.rw_gram_workspace_bytes(512, 512, 10890, 1) > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    from rewriting_b200 import ops
+    with pytest.raises(_cabi.RwError):
+        ops.prep_keys(torch.zeros(1, 64, 4, 4))
+    with pytest.raises(RuntimeError):
+        runningstats.RunningSecondMoment().add(torch.zeros(8, 128))
+
+
+def test_databag_semantics():
+    d = sg2.DataBag(latent=torch.zeros(1), fmap=torch.ones(2))
+    e = sg2.DataBag(d, fmap=torch.zeros(3))
+    assert e.fmap.shape == (3,) and d.fmap.shape == (2,)      # copy-on-construct
+    assert e.latent is d.latent
+    e.output = torch.ones(1)
+    assert 'output' in e and 'output' not in d
+    assert e.get('noise', None) is None
+    rebuilt = type(e)({k: v.detach() for k, v in e.items()})   # ganrewrite.py:708-729 idiom
+    assert isinstance(rebuilt, sg2.DataBag) and set(rebuilt) == set(e)
+    del e.output
+    assert 'output' not in e
+    with pytest.raises(AttributeError):
+        _ = e.missing
+
+
+def test_module_tree_and_state_dict_keys(seeded_model):
+    sd = seeded_model.state_dict()
+    assert len(sd) == 136
+    assert sd['layer8.sconv.mconv.dconv.weight'].shape == (1, 512, 512, 3, 3)
+    assert sd['layer2.conv.mconv.dconv.weight'].shape == (1, 512, 512, 3, 3)
+    assert sd['layer13.sconv.mconv.dconv.weight'].shape == (1, 128, 256, 3, 3)
+    assert sd['layer13.sconv.mconv.blur.kernel'].shape == (4, 4)
+    assert sd['to_rgb7.rgb.conv.weight'].shape == (1, 3, 128, 1, 1)
+    assert sd['latents.latent_avg'].ndim == 0
+    assert sd['noises.noise_12'].shape == (1, 1, 256, 256)
+    assert sum(p.numel() for p in seeded_model.parameters()) == 30034338
+    names = [n for n, _ in seeded_model.named_children()]
+    assert names[:7] == ['bag_in', 'style', 'latents', 'noises', 'input', 'layer2', 'to_rgb1']
+    assert names[-1] == 'output'
+
+
+def test_subsequence_split_matches_reference_structure(seeded_model):
+    first, last = 'layer8.sconv.mconv.dconv', 'layer8.sconv.activate'
+    ctx = nethook.subsequence(seeded_model, upto_layer=first, share_weights=True)
+    tgt = nethook.subsequence(seeded_model, first_layer=first, last_layer=last,
+                              share_weights=True)
+    rnd = nethook.subsequence(seeded_model, after_layer=last, share_weights=True)
+    leaf = lambda m: [n for n, c in m.named_modules() if len(list(c.children())) == 0]
+    assert [n for n, _ in ctx.named_children()][-1] == 'layer8'
+    assert [n for n, _ in ctx.layer8.named_children()] == ['lat6', 'sconv']
+    assert [n for n, _ in ctx.layer8.sconv.mconv.named_children()] == ['modulation', 'adain']
+    assert leaf(tgt) == ['layer8.sconv.mconv.dconv', 'layer8.sconv.noise', 'layer8.sconv.activate']
+    assert [n for n, _ in rnd.named_children()][:3] == ['to_rgb4', 'up_rgb4', 'layer9']
+    # whole children are the original objects, entered levels are plain Sequentials
+    assert ctx.layer7 is seeded_model.layer7
+    assert type(tgt.layer8.sconv) is torch.nn.Sequential
+    assert tgt.layer8.sconv.mconv.dconv is seeded_model.layer8.sconv.mconv.dconv
+    n = lambda m: len(m.state_dict())
+    assert n(ctx) + n(tgt) + n(rnd) == 136
+    with pytest.raises(ValueError):
+        nethook.subsequence(seeded_model, first_layer='layer99')
+    one = nethook.subsequence(seeded_model, single_layer='layer4', share_weights=False)
+    assert one.layer4 is not seeded_model.layer4
+
+
+def test_instrumented_model_hooks_and_unhooks():
+    net = torch.nn.Sequential()
+    net.add_module('a', torch.nn.Linear(4, 4))
+    net.add_module('b', torch.nn.ReLU())
+    x = torch.randn(2, 4)
+    with nethook.InstrumentedModel(net) as inst:
+        inst.retain_layer('a')
+        inst.edit_layer('b', ablation=1.0, replacement=torch.zeros(4))
+        y = inst(x)
+        assert torch.equal(y, torch.zeros(2, 4))
+        assert torch.allclose(inst.retained_layer('a'), net.a(x))
+        assert 'forward' in net.a.__dict__
+        only_a = inst(x, layer='a')
+        assert torch.allclose(only_a, net.a(x))
+    assert 'forward' not in net.a.__dict__ and 'forward' not in net.__dict__
+    assert (net(x) >= 0).all()
+
+
+def test_z_samples_are_prefix_stable():
+    a = zdataset.standard_z_sample(5, 512, seed=1)
+    b = zdataset.standard_z_sample(50, 512, seed=1)
+    assert a.dtype == torch.float32 and torch.equal(a, b[:5])
+    ref = np.random.RandomState(1).standard_normal(5 * 512).reshape(5, 512).astype('float32')
+    assert np.array_equal(a.numpy(), ref)
+
+
+def test_mask_decoding_uses_red_channel(edit_request):
+    url = edit_request['object'][1]
+    area = renormalize.from_url(url, target='pt', size=(32, 32))[0]
+    assert area.shape == (32, 32) and 0 < float(area.sum()) < 32 * 32
+    assert float(area.max()) == 1.0 and float(area.min()) == 0.0
+    full = renormalize.from_url(url, target='pt')
+    assert full.shape == (3, 256, 256)
+    t, l, b, r = ganrewrite.positive_bounding_box(area)
+    assert 0 <= t < b <= 32 and 0 <= l < r <= 32
+    assert ganrewrite.positive_bounding_box(torch.zeros(4, 4)) == (0, 0, 0, 0)
+
+
+def test_paste_and_crop_helpers():
+    src = torch.zeros(1, 2, 8, 8)
+    clip = torch.ones(1, 2, 3, 3)
+    out, (t, l, b, r) = ganrewrite.paste_clip_at_center(src, clip, (7, 0))
+    assert (t, l, b, r) == (5, 0, 8, 3) and out[0, 0, 5:8, 0:3].sum() == 9 and out.sum() == 18
+    half = torch.full((3, 3), 0.5)
+    out2, _ = ganrewrite.paste_clip_at_center(src + 2, clip, (4, 4), half)
+    assert torch.allclose(out2[0, 0, 3:6, 3:6], torch.full((3, 3), 1.5))
+    s, tg, sb, tb = ganrewrite.crop_clip_to_bounds(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 8, 8),
+                                                   (1, 2, 5, 7))
+    assert sb == (0, 1, 3, 4) and tb == (0, 2, 6, 8)
+    assert s.shape[2:] == (3, 3) and tg.shape[2:] == (6, 6)
+
+
+def test_second_moment_cache_format_roundtrip(tmp_path):
+    r = runningstats.RunningSecondMoment()
+    r.count, r.mom2 = 256000, torch.eye(8) * 3
+    path = str(tmp_path / 'cache' / 'r2m.npz')
+    tally.save_cached_state(path, r, dict(sample_size=None))
+    dat = np.load(path, allow_pickle=True)
+    assert set(dat.files) == {'constructor', 'count', 'mom2', 'sample_size'}
+    assert str(dat['constructor']).endswith('runningstats.RunningSecondMoment()')
+    assert dat['mom2'].dtype == np.float32
+    back = tally.load_cached_state(path, dict(sample_size=None))
+    r2 = runningstats.RunningSecondMoment(state=back)
+    assert r2.count == 256000 and torch.equal(r2.moment(), torch.eye(8) * 3 / 256000)
+    assert tally.load_cached_state(path, dict(sample_size=7)) is None    # args changed
+    # tally_second_moment returns the cached object without calling compute
+    out = tally.tally_second_moment(lambda z: 1 / 0, torch.zeros(4, 2), cachefile=path)
+    assert out.count == 256000
+
+
+def test_zca_from_cov_whitens():
+    torch.manual_seed(0)
+    a = torch.randn(4000, 16) @ torch.randn(16, 16)
+    C = a.t() @ a / 4000
+    Z = ganrewrite.zca_from_cov(C)
+    assert torch.allclose(Z @ C @ Z, torch.eye(16), atol=2e-3)
+    assert torch.allclose(Z, Z.t(), atol=1e-5)
+
+
+def test_checkpoint_key_conversion_from_rosinality_names(seeded_model):
+    sd = seeded_model.state_dict()
+
+    def back(k):   # inverse of the loader's renaming, for the keys it handles
+        k = re.sub(r'^layer2\.conv\.mconv\.dconv\.weight$', 'conv1.conv.weight', k)
+        k = re.sub(r'^layer2\.conv\.mconv\.', 'conv1.conv.', k)
+        k = re.sub(r'^layer2\.conv\.', 'conv1.', k)
+        m = re.match(r'^layer(\d+)\.sconv\.mconv\.dconv\.weight$', k)
+        if m:
+            return 'convs.%d.conv.weight' % (int(m.group(1)) - 3)
+        k = re.sub(r'^layer(\d+)\.sconv\.mconv\.', lambda m: 'convs.%d.conv.' % (int(m.group(1)) - 3), k)
+        k = re.sub(r'^layer(\d+)\.sconv\.', lambda m: 'convs.%d.' % (int(m.group(1)) - 3), k)
+        k = re.sub(r'^to_rgb1\.rgb\.', 'to_rgb1.', k)
+        k = re.sub(r'^up_rgb(\d+)\.', lambda m: 'to_rgbs.%d.upsample.' % (int(m.group(1)) - 1), k)
+        k = re.sub(r'^to_rgb(\d+)\.rgb\.', lambda m: 'to_rgbs.%d.' % (int(m.group(1)) - 2), k)
+        return k
+    ros = {back(k): v for k, v in sd.items() if not k.startswith(('noises', 'latents'))}
+    fresh = sg2.SeqStyleGAN2(256, 512, 8, mconv='seq')
+    fresh.load_state_dict({'g_ema': ros, 'latent_avg': torch.zeros(512)})
+    got = fresh.state_dict()
+    for k in sd:
+        if k == 'latents.latent_avg' or k.startswith('noises'):
+            continue
+        assert torch.equal(got[k], sd[k]), k
+    assert got['latents.latent_avg'].shape == (512,)
