@@ -92,6 +92,7 @@ static int gram_splits(int tiles, long long rows, int ntaps) {
   if (s > total_rb) s = total_rb;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
+  (void)0;
   return static_cast<int>(s);
 }
 

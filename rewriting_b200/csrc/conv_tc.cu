@@ -34,6 +34,14 @@ constexpr int BK = 64;            // bf16 elements per k-block = one 128B swizzl
 constexpr int UMMA_K = 16;
 constexpr int kStages = 3;
 constexpr int kNumThreads = 192;
+// The tensor core's fp32 accumulate truncates (round-toward-zero) on every MMA: measured
+// relative bias ~ -2^-25 per accumulation (profiles/r1_precision_probe.json), i.e. 1.6e-5
+// after the 864 accumulations of a K=4608 tile.  So a TMEM accumulator only ever holds a
+// CHUNK of kChunkKB k-blocks (K=512: 96 accumulations); the epilogue warps add the chunks in
+// fp32 registers with round-to-nearest.  kNumAcc TMEM buffers form a ring between the MMA
+// issuer and the epilogue.
+constexpr int kChunkKB = 8;
+constexpr int kNumAcc = 4;
 
 template <int BN>
 struct ConvSmem {
@@ -46,8 +54,8 @@ struct ConvSmem {
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[kNumAcc];
+  uint64_t tmem_empty[kNumAcc];
   uint32_t tmem_base;
 };
 
@@ -81,14 +89,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kNumAcc; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], 4);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<2 * BN>(&bars->tmem_base);
+    tmem_alloc<kNumAcc * BN>(&bars->tmem_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -125,35 +133,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+    uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       if (lane == 0) {
-        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
+          const int as = chunk % kNumAcc;
+          const uint32_t aphase = (chunk / kNumAcc) & 1u;
+          mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-          const uint64_t da_hi = make_smem_desc(sa, 16, 1024, kSwizzle128B);
-          const uint64_t da_lo = make_smem_desc(sa + S::kABytes, 16, 1024, kSwizzle128B);
-          const uint64_t db_hi = make_smem_desc(sa + 2 * S::kABytes, 16, 1024, kSwizzle128B);
-          const uint64_t db_lo =
-              make_smem_desc(sa + 2 * S::kABytes + S::kBBytes, 16, 1024, kSwizzle128B);
+          const uint32_t tmem_d = tmem_base + as * BN;
+          const int kb_end = (kb0 + kChunkKB < num_kb) ? kb0 + kChunkKB : num_kb;
+          for (int kb = kb0; kb < kb_end; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+            const uint64_t da_hi = make_smem_desc(sa, 16, 1024, kSwizzle128B);
+            const uint64_t da_lo = make_smem_desc(sa + S::kABytes, 16, 1024, kSwizzle128B);
+            const uint64_t db_hi = make_smem_desc(sa + 2 * S::kABytes, 16, 1024, kSwizzle128B);
+            const uint64_t db_lo =
+                make_smem_desc(sa + 2 * S::kABytes + S::kBBytes, 16, 1024, kSwizzle128B);
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
-            // smallest terms first, then the dominant hi*hi product
-            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | kk) != 0);
-            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
+              // smallest terms first, then the dominant hi*hi product
+              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+              umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+            umma_commit(&bars->empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&bars->empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          umma_commit(&bars->tmem_full[as]);
         }
-        umma_commit(&bars->tmem_full[as]);
       }
       __syncwarp();
     }
@@ -161,10 +172,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     // ------------------------------ epilogue ----------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int img = p.Hp * p.Wp;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+    uint32_t chunk = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n0 = (tile % n_tiles) * BN;
       const int m0 = (tile / n_tiles) * BM;
       const int prow = m0 + q * 32 + lane;
@@ -182,31 +191,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     static_cast<size_t>(xx) * p.out_sx;
       const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
 
-      mbar_wait(&bars->tmem_full[as], aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN + c0) +
-                               (static_cast<uint32_t>(q * 32) << 16);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
-        if (valid) {
+      float acc[BN];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int o = n0 + c0 + j;
-            float t = __uint_as_float(v[j]);
-            if (scl) t *= __ldg(scl + o);
-            t += nz;
-            if (p.bias) t += __ldg(p.bias + o);
-            if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
-            outp[static_cast<size_t>(o) * p.out_sc] = t;
-          }
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+
+      for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
+        const int as = chunk % kNumAcc;
+        const uint32_t aphase = (chunk / kNumAcc) & 1u;
+        mbar_wait(&bars->tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN + c0) +
+                                 (static_cast<uint32_t>(q * 32) << 16);
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      }
+
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < BN; ++j) {
+          const int o = n0 + j;
+          float t = acc[j];
+          if (scl) t *= __ldg(scl + o);
+          t += nz;
+          if (p.bias) t += __ldg(p.bias + o);
+          if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
+          outp[static_cast<size_t>(o) * p.out_sc] = t;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
     }
   }
 
@@ -214,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<kNumAcc * BN>(tmem_base);
   }
 }
 

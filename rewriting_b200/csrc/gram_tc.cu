@@ -28,6 +28,11 @@ constexpr int RB = 64;            // rows (contraction) per pipeline stage
 constexpr int UMMA_K = 16;
 constexpr int kStages = 3;
 constexpr int kNumThreads = 192;
+// fp32 accumulation in the tensor core truncates (see conv_tc.cu): a TMEM accumulator holds
+// at most kChunkRB row-blocks (1024 rows = 192 accumulations); chunks are summed in fp32
+// registers (round-to-nearest) by the epilogue warps.
+constexpr int kChunkRB = 16;
+constexpr int kNumAcc = 4;
 constexpr int kBlockBytes = 64 * RB * 2;       // one 64-channel x RB-row box
 constexpr int kPlaneBytes = (TM / 64) * kBlockBytes;
 constexpr int kStageBytes = 4 * kPlaneBytes;   // A_hi, A_lo, B_hi, B_lo
@@ -36,7 +41,8 @@ constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 256;
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t tmem_full;
+  uint64_t tmem_full[kNumAcc];
+  uint64_t tmem_empty[kNumAcc];
   uint32_t tmem_base;
 };
 
@@ -90,10 +96,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
-    mbar_init(&bars->tmem_full, 1);
+    for (int s = 0; s < kNumAcc; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TN>(&bars->tmem_base);
+  if (warp == 1) tmem_alloc<kNumAcc * TN>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,55 +136,69 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int i = 0; i < num_rb; ++i) {
-        mbar_wait(&bars->full[stage], phase);
+      uint32_t chunk = 0;
+      for (int i0 = 0; i0 < num_rb; i0 += kChunkRB, ++chunk) {
+        const int as = chunk % kNumAcc;
+        const uint32_t aphase = (chunk / kNumAcc) & 1u;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint64_t da_hi = make_smem_desc(sa, lbo_bytes, sbo_bytes, kSwizzle128B);
-        const uint64_t da_lo = make_smem_desc(sa + kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
-        const uint64_t db_hi =
-            make_smem_desc(sa + 2 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
-        const uint64_t db_lo =
-            make_smem_desc(sa + 3 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
+        const uint32_t tmem_d = tmem_base + as * TN;
+        const int i_end = (i0 + kChunkRB < num_rb) ? i0 + kChunkRB : num_rb;
+        for (int i = i0; i < i_end; ++i) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da_hi = make_smem_desc(sa, lbo_bytes, sbo_bytes, kSwizzle128B);
+          const uint64_t da_lo =
+              make_smem_desc(sa + kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
+          const uint64_t db_hi =
+              make_smem_desc(sa + 2 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
+          const uint64_t db_lo =
+              make_smem_desc(sa + 3 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
 #pragma unroll
-        for (int kk = 0; kk < RB / UMMA_K; ++kk) {
-          // 16 rows = two 8-row swizzle groups of 1024 B
-          const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 128) >> 4);
-          umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, (i | kk) != 0);
-          umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+          for (int kk = 0; kk < RB / UMMA_K; ++kk) {
+            // 16 rows = two 8-row swizzle groups of 1024 B
+            const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 128) >> 4);
+            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((i - i0) | kk) != 0);
+            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        umma_commit(&bars->tmem_full[as]);
       }
-      umma_commit(&bars->tmem_full);
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     float* dst = p.partial + (static_cast<size_t>(split) * p.Cm + row) * p.ldp + col_ofs + n0;
-    if (num_rb > 0) {
-      mbar_wait(&bars->tmem_full, 0);
+    float acc[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+    uint32_t chunk = 0;
+    for (int i0 = 0; i0 < num_rb; i0 += kChunkRB, ++chunk) {
+      const int as = chunk % kNumAcc;
+      const uint32_t aphase = (chunk / kNumAcc) & 1u;
+      mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < TN; c0 += 32) {
-      uint32_t v[32];
-      if (num_rb > 0) {
-        tmem_ld_32x32(tmem_base + static_cast<uint32_t>(c0) + (static_cast<uint32_t>(q * 32) << 16),
-                      v);
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + static_cast<uint32_t>(as * TN + c0) +
+                          (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
-      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o4 = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        *reinterpret_cast<float4*>(dst + c0 + j) = o4;
-      }
+    for (int j = 0; j < TN; j += 4) {
+      *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
   }
 
@@ -183,7 +206,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TN>(tmem_base);
+    tmem_dealloc<kNumAcc * TN>(tmem_base);
   }
 }
 
