@@ -71,35 +71,41 @@ def measured_peaks():
 
 
 class ClockSampler(object):
+    """Polls nvidia-smi (one-shot queries from a thread: its -lms loop block-buffers when
+    piped) for SM clocks and throttle reasons while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                for ln in out.stdout.strip().splitlines():
+                    self.rows.append([p.strip() for p in ln.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index),
-                 '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-                 'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '200'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=6)
         sm, mx, reasons = [], None, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(',')]
+        for parts in self.rows:
             if len(parts) < 6:
                 continue
             try:
@@ -107,12 +113,19 @@ class ClockSampler(object):
                 mx = float(parts[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[2:6]):
+            for nm, v in zip(self.NAMES, parts[2:6]):
                 if v.lower().startswith('active'):
                     reasons.add(nm)
         sm.sort()
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx,
                     reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_threads():
+    """torch CPU convs at batch 2 stop scaling past ~16 threads (measured on the 128-core GPU
+    host: 8 thr 1.11 s, 16 thr 0.96 s, 32 thr 0.98 s, 64 thr 1.41 s, 128 thr 19 s per forward),
+    so the baseline uses the fastest setting, not the core count."""
+    return max(1, min(os.cpu_count() or 1, 16))
 
 
 def build_model(device):
@@ -127,7 +140,7 @@ def cpu_baseline_generator(seconds=12.0, batch=2):
     from oracle import sg2_oracle as orc
     from rewriting_b200.utils.stylegan2 import SeqStyleGAN2
     from rewriting_b200.utils import zdataset
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     model = orc.seeded_state_dict(lambda: SeqStyleGAN2(SIZE, style_dim=512, n_mlp=8, mconv='seq'))
     sd = {k: v for k, v in model.state_dict().items()}
@@ -154,7 +167,7 @@ def run_reference(args):
     from oracle import sg2_oracle as orc
     from rewriting_b200.utils.stylegan2 import SeqStyleGAN2
     from rewriting_b200.utils import zdataset
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     model = orc.seeded_state_dict(lambda: SeqStyleGAN2(SIZE, style_dim=512, n_mlp=8, mconv='seq'))
     sd = dict(model.state_dict())
