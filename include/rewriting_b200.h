@@ -75,23 +75,25 @@ int rw_demod(const float* style, const float* wsq, int B, int Cout, int Cin, flo
              float* demod, rw_stream_t stream);
 
 /* ---- fused modulated 3x3 convolution (tcgen05) ---- */
-/* out[b,o,y,x] = act( conv3x3(k, scale*W)[b,o,y,x] * scale_bo[b,o] + noise_w*noise[b,y*W+x] + bias[o] )
- * scale_bo / noise / bias may be NULL; act: 0 none, 1 leaky_relu(0.2)*sqrt(2). */
+/* out[b,o,y,x] = act( conv3x3(k, scale*W)[b,o,y,x] * scale_bo[b,o] + noise_w[0]*noise[b,y*W+x] + bias[o] )
+ * scale_bo / noise / bias may be NULL; noise_w is a DEVICE scalar (the nn.Parameter's storage,
+ * so no host sync per layer); act: 0 none, 1 leaky_relu(0.2)*sqrt(2). */
 int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                    const float* scale_bo, const float* noise, long long noise_bstride,
-                   float noise_w, const float* bias, int act, int B, int Cin, int Cout, int H,
-                   int W, float* out, rw_stream_t stream);
+                   const float* noise_w, const float* bias, int act, int B, int Cin, int Cout,
+                   int H, int W, float* out, rw_stream_t stream);
 /* t[b,o,:,:] = conv_transpose2d(k, (scale*W)^T, stride 2, pad 0)[b,o] * scale_bo[b,o]; out is
- * [B,Cout,2H+1,2W+1].  Four polyphase launches, exact algorithmic FLOPs. */
+ * [B,Cout,2H+1,2W+1].  One launch: the four polyphase components are tile-interleaved (exact
+ * algorithmic FLOPs, A tiles shared through L2). */
 int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                       const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
                       rw_stream_t stream);
 /* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
-                   const float* noise, long long noise_bstride, float noise_w, const float* bias,
-                   int act, float* y, rw_stream_t stream);
-int rw_add_noise(const float* x, const float* noise, long long noise_bstride, float noise_w,
-                 int B, int C, int HW, float* y, rw_stream_t stream);
+                   const float* noise, long long noise_bstride, const float* noise_w,
+                   const float* bias, int act, float* y, rw_stream_t stream);
+int rw_add_noise(const float* x, const float* noise, long long noise_bstride,
+                 const float* noise_w, int B, int C, int HW, float* y, rw_stream_t stream);
 int rw_torgb(const float* x, const float* style, const float* w, const float* bias,
              const float* skip, int B, int C, int H, int W, float scale, float* out,
              rw_stream_t stream);

@@ -146,9 +146,9 @@ int rw_demod(const float* style, const float* wsq, int B, int Cout, int Cin, flo
 
 int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                    const float* scale_bo, const float* noise, long long noise_bstride,
-                   float noise_w, const float* bias, int act, int B, int Cin, int Cout, int H,
-                   int W, float* out, rw_stream_t stream) {
-  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !out || B < 1) {
+                   const float* noise_w, const float* bias, int act, int B, int Cin, int Cout,
+                   int H, int W, float* out, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !out || B < 1 || (noise && !noise_w)) {
     set_last_error("rw_modconv_fwd: bad argument");
     return RW_ERR_BAD_ARG;
   }
@@ -156,8 +156,9 @@ int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, cons
   memset(&p, 0, sizeof(p));
   p.Hp = H + 1;
   p.Wp = W + 1;
-  p.Hv = H;
-  p.Wv = W;
+  p.nphase = 1;
+  p.ph_Hv[0] = H;
+  p.ph_Wv[0] = W;
   const long long rows = static_cast<long long>(B) * p.Hp * p.Wp;
   if (rows > 0x7fffffffLL) {
     set_last_error("rw_modconv_fwd: too many rows");
@@ -166,11 +167,11 @@ int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, cons
   p.rows = static_cast<int>(rows);
   p.Cin = Cin;
   p.Cout = Cout;
-  p.ntaps = 9;
+  p.ph_ntaps[0] = 9;
   for (int u = 0; u < 3; ++u)
     for (int v = 0; v < 3; ++v) {
-      p.tap_shift[u * 3 + v] = (u - 1) * p.Wp + (v - 1);
-      p.tap_kofs[u * 3 + v] = (u * 3 + v) * Cin;
+      p.ph_shift[0][u * 3 + v] = (u - 1) * p.Wp + (v - 1);
+      p.ph_kofs[0][u * 3 + v] = (u * 3 + v) * Cin;
     }
   p.scale_bo = scale_bo;
   p.bias = bias;
@@ -203,47 +204,50 @@ int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, c
     set_last_error("rw_modconv_up_fwd: too many rows");
     return RW_ERR_BAD_ARG;
   }
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Hp = Hp;
+  p.Wp = Wp;
+  p.rows = static_cast<int>(rows);
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.nphase = 4;
+  p.scale_bo = scale_bo;
+  p.out = t_out;
+  p.out_sb = static_cast<long long>(Cout) * Ht * Wt;
+  p.out_sc = static_cast<long long>(Ht) * Wt;
+  p.out_sy = 2LL * Wt;
+  p.out_sx = 2;
+  // heaviest phase first within every (m, n) group: (0,0) has 4 taps, (1,1) has 1
   for (int a = 0; a < 2; ++a) {
     for (int b = 0; b < 2; ++b) {
-      ConvTcParams p;
-      memset(&p, 0, sizeof(p));
-      p.Hp = Hp;
-      p.Wp = Wp;
-      p.Hv = Hp - a;
-      p.Wv = Wp - b;
-      p.rows = static_cast<int>(rows);
-      p.Cin = Cin;
-      p.Cout = Cout;
+      const int ph = a * 2 + b;
+      p.ph_Hv[ph] = Hp - a;
+      p.ph_Wv[ph] = Wp - b;
+      p.ph_out_ofs[ph] = static_cast<long long>(a) * Wt + b;
       int us[2], dys[2], nu;
       int vs[2], dxs[2], nv;
       if (a == 0) { nu = 2; us[0] = 0; dys[0] = 0; us[1] = 2; dys[1] = -1; }
       else        { nu = 1; us[0] = 1; dys[0] = 0; }
       if (b == 0) { nv = 2; vs[0] = 0; dxs[0] = 0; vs[1] = 2; dxs[1] = -1; }
       else        { nv = 1; vs[0] = 1; dxs[0] = 0; }
-      p.ntaps = 0;
+      int n = 0;
       for (int iu = 0; iu < nu; ++iu)
         for (int iv = 0; iv < nv; ++iv) {
-          p.tap_shift[p.ntaps] = dys[iu] * Wp + dxs[iv];
-          p.tap_kofs[p.ntaps] = (us[iu] * 3 + vs[iv]) * Cin;
-          ++p.ntaps;
+          p.ph_shift[ph][n] = dys[iu] * Wp + dxs[iv];
+          p.ph_kofs[ph][n] = (us[iu] * 3 + vs[iv]) * Cin;
+          ++n;
         }
-      p.scale_bo = scale_bo;
-      p.out = t_out + static_cast<long long>(a) * Wt + b;
-      p.out_sb = static_cast<long long>(Cout) * Ht * Wt;
-      p.out_sc = static_cast<long long>(Ht) * Wt;
-      p.out_sy = 2LL * Wt;
-      p.out_sx = 2;
-      int rc = conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
-      if (rc) return rc;
+      p.ph_ntaps[ph] = n;
     }
   }
-  return RW_OK;
+  return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
 }
 
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
-                   const float* noise, long long noise_bstride, float noise_w, const float* bias,
-                   int act, float* y, rw_stream_t stream) {
-  if (!t || !kernel4x4 || !y) {
+                   const float* noise, long long noise_bstride, const float* noise_w,
+                   const float* bias, int act, float* y, rw_stream_t stream) {
+  if (!t || !kernel4x4 || !y || (noise && !noise_w)) {
     set_last_error("rw_blur_up_act: bad argument");
     return RW_ERR_BAD_ARG;
   }
@@ -251,9 +255,9 @@ int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* 
                             y, stream);
 }
 
-int rw_add_noise(const float* x, const float* noise, long long noise_bstride, float noise_w,
-                 int B, int C, int HW, float* y, rw_stream_t stream) {
-  if (!x || !noise || !y) {
+int rw_add_noise(const float* x, const float* noise, long long noise_bstride,
+                 const float* noise_w, int B, int C, int HW, float* y, rw_stream_t stream) {
+  if (!x || !noise || !y || !noise_w) {
     set_last_error("rw_add_noise: bad argument");
     return RW_ERR_BAD_ARG;
   }
@@ -402,8 +406,8 @@ int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const
                      int rows, int K, int N, float* out, rw_stream_t stream) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
-  p.rows = rows; p.Cin = K; p.Cout = N; p.ntaps = 1;
-  p.Hp = 1; p.Wp = rows; p.Hv = 1; p.Wv = rows;   // one "image" = all rows
+  p.rows = rows; p.Cin = K; p.Cout = N; p.nphase = 1; p.ph_ntaps[0] = 1;
+  p.Hp = 1; p.Wp = rows; p.ph_Hv[0] = 1; p.ph_Wv[0] = rows;   // one "image" = all rows
   p.out = out; p.out_sb = 0; p.out_sc = 1; p.out_sy = 0; p.out_sx = N;  // row-major [rows][N]
   return conv_tc_launch(p, a_hi, a_lo, w_hi, w_lo, K, stream);
 }

@@ -76,9 +76,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 
   const int m_tiles = (p.rows + BM - 1) / BM;
   const int n_tiles = p.Cout / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * p.nphase;
   const int kb_per_tap = p.Cin / BK;
-  const int num_kb = p.ntaps * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -109,11 +109,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * BN;
-        const int m0 = (tile / n_tiles) * BM;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int arow = m0 + p.tap_shift[t];
-          const int wcol = p.tap_kofs[t];
+        const int ph = tile % p.nphase;
+        const int mn = tile / p.nphase;
+        const int n0 = (mn % n_tiles) * BN;
+        const int m0 = (mn / n_tiles) * BM;
+        for (int t = 0; t < p.ph_ntaps[ph]; ++t) {
+          const int arow = m0 + p.ph_shift[ph][t];
+          const int wcol = p.ph_kofs[ph][t];
           for (int kb = 0; kb < kb_per_tap; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             uint8_t* st = smem + stage * S::kStageBytes;
@@ -135,6 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int num_kb = p.ph_ntaps[tile % p.nphase] * kb_per_tap;
       if (lane == 0) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
           const int as = chunk % kNumAcc;
@@ -174,21 +177,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int img = p.Hp * p.Wp;
     uint32_t chunk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n0 = (tile % n_tiles) * BN;
-      const int m0 = (tile / n_tiles) * BM;
+      const int ph = tile % p.nphase;
+      const int mn = tile / p.nphase;
+      const int num_kb = p.ph_ntaps[ph] * kb_per_tap;
+      const int Hv = p.ph_Hv[ph], Wv = p.ph_Wv[ph];
+      const int n0 = (mn % n_tiles) * BN;
+      const int m0 = (mn / n_tiles) * BM;
       const int prow = m0 + q * 32 + lane;
       const int b = prow / img;
       const int rem = prow - b * img;
       const int yy = rem / p.Wp;
       const int xx = rem - yy * p.Wp;
-      const bool valid = (prow < p.rows) && (yy < p.Hv) && (xx < p.Wv);
+      const bool valid = (prow < p.rows) && (yy < Hv) && (xx < Wv);
       float nz = 0.f;
       if (valid && p.noise != nullptr) {
-        nz = p.noise_w * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
-                               static_cast<size_t>(yy) * p.Wv + xx);
+        nz = __ldg(p.noise_w) * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
+                                      static_cast<size_t>(yy) * Wv + xx);
       }
-      float* outp = p.out + static_cast<size_t>(b) * p.out_sb + static_cast<size_t>(yy) * p.out_sy +
-                    static_cast<size_t>(xx) * p.out_sx;
+      float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
+                    static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
       const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
 
       float acc[BN];
@@ -243,11 +250,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
                    const void* w_lo, int wk_total, cudaStream_t stream) {
   constexpr int BN = 128;
-  if (p.Cin % BK != 0 || p.Cout % BN != 0 || p.ntaps < 1 || p.ntaps > 9 || p.rows <= 0) {
-    set_last_error("conv_tc: unsupported shape Cin=%d Cout=%d ntaps=%d rows=%d", p.Cin, p.Cout,
-                   p.ntaps, p.rows);
+  if (p.Cin % BK != 0 || p.Cout % BN != 0 || p.nphase < 1 || p.nphase > 4 || p.rows <= 0) {
+    set_last_error("conv_tc: unsupported shape Cin=%d Cout=%d nphase=%d rows=%d", p.Cin, p.Cout,
+                   p.nphase, p.rows);
     return RW_ERR_BAD_ARG;
   }
+  for (int i = 0; i < p.nphase; ++i)
+    if (p.ph_ntaps[i] < 1 || p.ph_ntaps[i] > 9) {
+      set_last_error("conv_tc: phase %d has %d taps", i, p.ph_ntaps[i]);
+      return RW_ERR_BAD_ARG;
+    }
   CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
   int rc;
   if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, p.Cin, p.rows, (uint64_t)p.Cin * 2, BK, BM))) return rc;
@@ -268,7 +280,7 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
   }
   const int m_tiles = (p.rows + BM - 1) / BM;
   const int n_tiles = p.Cout / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_tiles * n_tiles * p.nphase;
   int grid = device_sm_count();
   if (grid > num_tiles) grid = num_tiles;
   conv_tc_kernel<BN><<<grid, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);

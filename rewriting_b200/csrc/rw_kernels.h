@@ -14,17 +14,22 @@ struct ConvTcParams {
   int rows;          // padded-flat rows = B * Hp * Wp  (GEMM M)
   int Cin;           // GEMM K per tap
   int Cout;          // GEMM N
-  int ntaps;
-  int tap_shift[9];  // row shift applied to the A operand for this tap
-  int tap_kofs[9];   // column offset of this tap inside the weight matrix
+  // Up to 4 "phases" share one launch (the 4 polyphase components of a stride-2
+  // conv_transpose): tile index = (m, n, phase) with phase fastest, so the CTAs that
+  // run concurrently read the same A tiles (L2 hits instead of 4 DRAM passes).
+  int nphase;
+  int ph_ntaps[4];
+  int ph_shift[4][9];   // row shift applied to the A operand for this tap
+  int ph_kofs[4][9];    // column offset of this tap inside the weight matrix
+  int ph_Hv[4], ph_Wv[4];       // valid output extent inside the padded grid
+  long long ph_out_ofs[4];      // element offset of this phase's output origin
   int Hp, Wp;        // padded grid of one image
-  int Hv, Wv;        // valid output extent inside the padded grid
   // epilogue
   const float* scale_bo;  // [B, Cout] per-sample per-channel scale (demod / style) or null
   const float* bias;      // [Cout] or null
   const float* noise;     // [B, noise_bstride] or null, indexed y*Wv + x
   long long noise_bstride;
-  float noise_w;
+  const float* noise_w;   // device scalar (read by the kernel: no host sync per layer)
   int act;                // 1 -> leaky_relu(0.2) * sqrt(2)
   float* out;
   long long out_sb, out_sc, out_sy, out_sx;  // element strides: batch, channel, y, x
@@ -70,7 +75,7 @@ int prep_weights_launch(const float* w, int Cout, int Cin, float scale, int tran
 int demod_launch(const float* style, const float* wsq, int B, int Cout, int Cin, float eps,
                  float* demod, cudaStream_t stream);
 int blur_up_act_launch(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
-                       const float* noise, long long noise_bstride, float noise_w,
+                       const float* noise, long long noise_bstride, const float* noise_w,
                        const float* bias, int act, float* y, cudaStream_t stream);
 int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
                      int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
@@ -81,7 +86,7 @@ int bias_act_launch(const float* x, const float* bias, const float* ref, int act
 int torgb_launch(const float* x, const float* style, const float* w, const float* bias,
                  const float* skip, int B, int C, int H, int W, float scale, float* out,
                  cudaStream_t stream);
-int add_noise_launch(const float* x, const float* noise, long long noise_bstride, float noise_w,
+int add_noise_launch(const float* x, const float* noise, long long noise_bstride, const float* noise_w,
                      int B, int C, int HW, float* y, cudaStream_t stream);
 
 // rewrite (rewrite.cu)

@@ -153,8 +153,9 @@ __global__ void demod_kernel(const float* __restrict__ style, const float* __res
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 blur_up_act_kernel(const float* __restrict__ t, int C, int Ht, int Wt, const float* __restrict__ k4,
-                   const float* __restrict__ noise, long long noise_bstride, float noise_w,
-                   const float* __restrict__ bias, int act, float* __restrict__ y) {
+                   const float* __restrict__ noise, long long noise_bstride,
+                   const float* __restrict__ noise_w, const float* __restrict__ bias, int act,
+                   float* __restrict__ y) {
   constexpr int TX = 32, TY = 8;
   __shared__ float tile[TY + 3][TX + 3];
   __shared__ float kf[16];
@@ -182,7 +183,7 @@ blur_up_act_kernel(const float* __restrict__ t, int C, int Ht, int Wt, const flo
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb)
       acc = fmaf(tile[threadIdx.y + a][threadIdx.x + bb], kf[a * 4 + bb], acc);
-  if (noise) acc += noise_w * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
+  if (noise) acc += __ldg(noise_w) * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
                                     static_cast<size_t>(oy) * Wo + ox);
   if (bias) acc += __ldg(bias + c);
   if (act) acc = (acc > 0.f ? acc : 0.2f * acc) * 1.4142135623730951f;
@@ -292,9 +293,11 @@ torgb_kernel(const float* __restrict__ x, const float* __restrict__ style,
 
 // y[b,c,p] = x[b,c,p] + noise_w * noise[b,p]     (NoiseInjectionF, models.py:535-546)
 __global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
-                                 long long noise_bstride, float noise_w, int C, int HW,
+                                 long long noise_bstride, const float* __restrict__ noise_w_p,
+                                 int C, int HW,
                                  long long total, float* __restrict__ y) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const float noise_w = __ldg(noise_w_p);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += stride) {
     const int p = static_cast<int>(i % HW);
@@ -354,7 +357,7 @@ int demod_launch(const float* style, const float* wsq, int B, int Cout, int Cin,
 }
 
 int blur_up_act_launch(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
-                       const float* noise, long long noise_bstride, float noise_w,
+                       const float* noise, long long noise_bstride, const float* noise_w,
                        const float* bias, int act, float* y, cudaStream_t stream) {
   const int Ht = 2 * Hin + 1, Wt = 2 * Win + 1;
   const int Ho = 2 * Hin, Wo = 2 * Win;
@@ -407,7 +410,7 @@ int torgb_launch(const float* x, const float* style, const float* w, const float
   return check_cuda(cudaGetLastError(), "torgb launch");
 }
 
-int add_noise_launch(const float* x, const float* noise, long long noise_bstride, float noise_w,
+int add_noise_launch(const float* x, const float* noise, long long noise_bstride, const float* noise_w,
                      int B, int C, int HW, float* y, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * C * HW;
   if (total <= 0) return RW_OK;

@@ -1,0 +1,44 @@
+"""CUDA-graph capture of a fixed-shape forward (launch-bound inner loops).
+
+One generator forward at batch 32 is ~190 kernel launches (31 tensor-core convs plus the
+prep / blur / ToRGB / mapping kernels); captured once, a replay costs one launch.  The
+captured region is exactly the public module call — `GraphedModule(model, z)(z_new)` returns
+what `model(z_new)` returns — and is valid while the module's parameters keep their storage
+(in-place edits such as the rewriter's are picked up; the bf16 weight planes are refreshed
+by calling `refresh()` after an edit, which re-captures).
+"""
+import torch
+
+
+class GraphedModule(object):
+    def __init__(self, module, example_input, warmup=3):
+        if not example_input.is_cuda:
+            raise RuntimeError('GraphedModule needs a CUDA example input')
+        self.module = module
+        self.static_in = example_input.detach().clone()
+        self.graph = None
+        self.static_out = None
+        self._warmup = warmup
+        self.refresh()
+
+    def refresh(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self._warmup):       # fills the noise / weight-plane caches
+                self.module(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = self.module(self.static_in)
+
+    def __call__(self, x, out=None):
+        """Replays the forward on `x` (any device; copied into the static input).  Returns the
+        static output tensor (overwritten by the next call) or copies it into `out`."""
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        if out is not None:
+            out.copy_(self.static_out, non_blocking=True)
+            return out
+        return self.static_out

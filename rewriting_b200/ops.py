@@ -143,14 +143,14 @@ def demod_factors(style, wsq, eps=1e-8):
 
 
 # --------------------------------------------------------------------------- conv kernels
-def conv3x3_planes(planes, w_hi, w_lo, Cout, scale_bo=None, noise=None, noise_w=0.0, bias=None,
+def conv3x3_planes(planes, w_hi, w_lo, Cout, scale_bo=None, noise=None, noise_w=None, bias=None,
                    act=False):
     """row-GEMM 3x3 conv (pad 1) over key planes -> [B,Cout,H,W] fp32."""
     B, Cin, H, W = planes.B, planes.C, planes.H, planes.W
     out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=planes.hi.device)
     nstride = noise.stride(0) if noise is not None else 0
     _cabi.call('rw_modconv_fwd', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo), _p(scale_bo),
-               _p(noise), nstride, float(noise_w), _p(bias), 1 if act else 0, B, Cin, Cout, H, W,
+               _p(noise), nstride, _p(noise_w), _p(bias), 1 if act else 0, B, Cin, Cout, H, W,
                _p(out), _stream())
     return out
 
@@ -165,14 +165,14 @@ def convT3x3_planes(planes, w_hi, w_lo, Cout, scale_bo=None):
     return out
 
 
-def blur_up_act(t, kernel, noise=None, noise_w=0.0, bias=None, act=False):
+def blur_up_act(t, kernel, noise=None, noise_w=None, bias=None, act=False):
     t = _f32c(t)
     B, C, Ht, Wt = t.shape
     Hin, Win = (Ht - 1) // 2, (Wt - 1) // 2
     y = torch.empty((B, C, 2 * Hin, 2 * Win), dtype=torch.float32, device=t.device)
     nstride = noise.stride(0) if noise is not None else 0
     _cabi.call('rw_blur_up_act', _p(t), B, C, Hin, Win, _p(_f32c(kernel)), _p(noise), nstride,
-               float(noise_w), _p(bias), 1 if act else 0, _p(y), _stream())
+               _p(noise_w), _p(bias), 1 if act else 0, _p(y), _stream())
     return y
 
 
@@ -180,8 +180,8 @@ def add_noise(x, noise, noise_w):
     x = _f32c(x)
     B, C, H, W = x.shape
     y = torch.empty_like(x)
-    _cabi.call('rw_add_noise', _p(x), _p(noise), noise.stride(0), float(noise_w), B, C, H * W,
-               _p(y), _stream())
+    _cabi.call('rw_add_noise', _p(x), _p(noise), noise.stride(0), _p(_f32c(noise_w.detach())), B, C,
+               H * W, _p(y), _stream())
     return y
 
 
@@ -315,7 +315,10 @@ class StyledConvFunction(torch.autograd.Function):
             planes, _ = prep_keys(x, style)
         w_hi, w_lo, wsq = wholder.planes('fwd')
         dm = demod_factors(style, wsq) if demodulate else None
-        nw = float(noise_weight.detach().item()) if (with_noise and noise_weight is not None) else 0.0
+        # device scalar: the kernels read the Parameter's storage (no .item() host sync)
+        nw = _f32c(noise_weight.detach()) if (with_noise and noise_weight is not None) else None
+        if nw is None:
+            with_noise = False
         b = _f32c(bias.detach()) if (with_act and bias is not None) else None
         if upsample:
             t = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)

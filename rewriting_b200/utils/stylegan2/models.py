@@ -241,7 +241,7 @@ class NoiseInjectionF(nn.Module):
         else:
             if noise.stride(-1) != 1:
                 noise = noise.contiguous()
-            out = ops.add_noise(image, noise, float(self.weight.item()))
+            out = ops.add_noise(image, noise, self.weight)
         return DataBag(d, fmap=out)
 
 
