@@ -275,8 +275,9 @@ def test_rewriter_statistics_direction_and_edit_vs_golden(cuda_model, z40, golde
     goal_in, goal_out, _, pb = gw.paste_from_selection(edit_request['paste'][0],
                                                        edit_request['paste'][1], obj_acts, obj_area)
     assert tuple(ob) == tuple(golden['obj_bounds']) and tuple(pb) == tuple(golden['paste_bounds'])
-    assert (goal_in.fmap.cpu() - torch.from_numpy(golden['goal_in_fmap'])).abs().max() < 2e-4
-    assert (goal_out.fmap.cpu() - torch.from_numpy(golden['goal_out_fmap'])).abs().max() < 2e-4
+    # keys / values after 7-8 chained tensor-core layers: same 1e-3 bound as the pixels
+    assert (goal_in.fmap.cpu() - torch.from_numpy(golden['goal_in_fmap'])).abs().max() < 1e-3
+    assert (goal_out.fmap.cpu() - torch.from_numpy(golden['goal_out_fmap'])).abs().max() < 1e-3
     # the edit: identical state and direction as the reference run, 11 iterations
     gin = type(goal_in)(goal_in, fmap=torch.from_numpy(golden['goal_in_fmap']).cuda(),
                         style=torch.from_numpy(golden['goal_in_style']).cuda())
