@@ -88,6 +88,28 @@ int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, cons
 int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                       const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
                       rw_stream_t stream);
+/* ---- generation fast path: producers write the consumer's operands directly ----
+ * rw_modconv_fwd_fused = rw_modconv_fwd whose epilogue can additionally emit
+ *   next_{hi,lo}[rows][Cout] : key planes of the NEXT layer, split_bf16(next_scale[b,o] * y)
+ *   rgb_part[Cout/128][B][3][H*W] : this layer's ToRGB partial sums with rgb_w[B,3,Cout]
+ * `out` (fp32 NCHW) becomes optional.  rw_modconv_up_fwd_cl writes the conv_transpose output
+ * channels-last per phase, t_cl[4][rows][Cout]; rw_blur_up_fused turns it into the next layer's
+ * planes (and/or fp32 NCHW); rw_rgb_combine = sum of partials + bias + 2x-upsampled skip. */
+int rw_modconv_fwd_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                         const void* wt_lo, const float* scale_bo, const float* noise,
+                         long long noise_bstride, const float* noise_w, const float* bias, int act,
+                         int B, int Cin, int Cout, int H, int W, float* out,
+                         const float* next_scale, void* next_hi, void* next_lo,
+                         const float* rgb_w, float* rgb_part, rw_stream_t stream);
+int rw_modconv_up_fwd_cl(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                         const void* wt_lo, const float* scale_bo, int B, int Cin, int Cout, int H,
+                         int W, float* t_cl, rw_stream_t stream);
+int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const float* kernel4x4,
+                     const float* noise, long long noise_bstride, const float* noise_w,
+                     const float* bias, int act, const float* next_scale, void* next_hi,
+                     void* next_lo, float* y_out, rw_stream_t stream);
+int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
+                   const float* prev, const float* kernel4x4, float* out, rw_stream_t stream);
 /* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
                    const float* noise, long long noise_bstride, const float* noise_w,

@@ -49,6 +49,14 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     'rw_modconv_up_fwd': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
                                   c_p, c_p]),
+    'rw_modconv_fwd_fused': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p,
+                                     c_p, c_p, c_p]),
+    'rw_modconv_up_fwd_cl': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_p, c_p]),
+    'rw_blur_up_fused': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
+                                 c_int, c_p, c_p, c_p, c_p, c_p]),
+    'rw_rgb_combine': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
     'rw_blur_up_act': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                c_int, c_p, c_p]),
     'rw_add_noise': (c_int, [c_p, c_p, c_ll, c_p, c_int, c_int, c_int, c_p, c_p]),

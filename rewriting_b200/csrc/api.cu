@@ -156,6 +156,7 @@ int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, cons
   memset(&p, 0, sizeof(p));
   p.Hp = H + 1;
   p.Wp = W + 1;
+  p.B = B;
   p.nphase = 1;
   p.ph_Hv[0] = H;
   p.ph_Wv[0] = W;
@@ -187,9 +188,9 @@ int rw_modconv_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, cons
   return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
 }
 
-int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
-                      const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
-                      rw_stream_t stream) {
+static int modconv_up_impl(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                           const void* wt_lo, const float* scale_bo, int B, int Cin, int Cout,
+                           int H, int W, float* t_out, int channels_last, rw_stream_t stream) {
   if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !t_out || B < 1) {
     set_last_error("rw_modconv_up_fwd: bad argument");
     return RW_ERR_BAD_ARG;
@@ -208,6 +209,7 @@ int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, c
   memset(&p, 0, sizeof(p));
   p.Hp = Hp;
   p.Wp = Wp;
+  p.B = B;
   p.rows = static_cast<int>(rows);
   p.Cin = Cin;
   p.Cout = Cout;
@@ -218,6 +220,7 @@ int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, c
   p.out_sc = static_cast<long long>(Ht) * Wt;
   p.out_sy = 2LL * Wt;
   p.out_sx = 2;
+  p.out_mode = channels_last ? 1 : 0;
   // heaviest phase first within every (m, n) group: (0,0) has 4 taps, (1,1) has 1
   for (int a = 0; a < 2; ++a) {
     for (int b = 0; b < 2; ++b) {
@@ -242,6 +245,99 @@ int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, c
     }
   }
   return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
+}
+
+int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                      const float* scale_bo, int B, int Cin, int Cout, int H, int W, float* t_out,
+                      rw_stream_t stream) {
+  return modconv_up_impl(kp_hi, kp_lo, wt_hi, wt_lo, scale_bo, B, Cin, Cout, H, W, t_out, 0, stream);
+}
+
+int rw_modconv_up_fwd_cl(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                         const void* wt_lo, const float* scale_bo, int B, int Cin, int Cout, int H,
+                         int W, float* t_cl, rw_stream_t stream) {
+  return modconv_up_impl(kp_hi, kp_lo, wt_hi, wt_lo, scale_bo, B, Cin, Cout, H, W, t_cl, 1, stream);
+}
+
+static int fill_conv3x3(ConvTcParams& p, int B, int Cin, int Cout, int H, int W) {
+  memset(&p, 0, sizeof(p));
+  p.Hp = H + 1;
+  p.Wp = W + 1;
+  p.B = B;
+  p.nphase = 1;
+  p.ph_Hv[0] = H;
+  p.ph_Wv[0] = W;
+  const long long rows = static_cast<long long>(B) * p.Hp * p.Wp;
+  if (rows > 0x7fffffffLL) {
+    set_last_error("conv: too many rows");
+    return RW_ERR_BAD_ARG;
+  }
+  p.rows = static_cast<int>(rows);
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.ph_ntaps[0] = 9;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      p.ph_shift[0][u * 3 + v] = (u - 1) * p.Wp + (v - 1);
+      p.ph_kofs[0][u * 3 + v] = (u * 3 + v) * Cin;
+    }
+  p.out_sb = static_cast<long long>(Cout) * H * W;
+  p.out_sc = static_cast<long long>(H) * W;
+  p.out_sy = W;
+  p.out_sx = 1;
+  return RW_OK;
+}
+
+int rw_modconv_fwd_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                         const void* wt_lo, const float* scale_bo, const float* noise,
+                         long long noise_bstride, const float* noise_w, const float* bias, int act,
+                         int B, int Cin, int Cout, int H, int W, float* out,
+                         const float* next_scale, void* next_hi, void* next_lo,
+                         const float* rgb_w, float* rgb_part, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || B < 1 || (noise && !noise_w) ||
+      ((next_hi != nullptr) != (next_lo != nullptr)) || (next_hi && !next_scale) ||
+      ((rgb_w != nullptr) != (rgb_part != nullptr)) || (!out && !next_hi && !rgb_part)) {
+    set_last_error("rw_modconv_fwd_fused: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  ConvTcParams p;
+  int rc = fill_conv3x3(p, B, Cin, Cout, H, W);
+  if (rc) return rc;
+  p.scale_bo = scale_bo;
+  p.bias = bias;
+  p.noise = noise;
+  p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w;
+  p.act = act;
+  p.out = out;
+  p.next_hi = next_hi;
+  p.next_lo = next_lo;
+  p.next_scale = next_scale;
+  p.rgb_w = rgb_w;
+  p.rgb_part = rgb_part;
+  return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
+}
+
+int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const float* kernel4x4,
+                     const float* noise, long long noise_bstride, const float* noise_w,
+                     const float* bias, int act, const float* next_scale, void* next_hi,
+                     void* next_lo, float* y_out, rw_stream_t stream) {
+  if (!t_cl || !kernel4x4 || (noise && !noise_w) || ((next_hi != nullptr) != (next_lo != nullptr)) ||
+      (!next_hi && !y_out)) {
+    set_last_error("rw_blur_up_fused: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return blur_up_fused_launch(t_cl, B, C, Hin, Win, kernel4x4, noise, noise_bstride, noise_w, bias,
+                              act, next_scale, next_hi, next_lo, y_out, stream);
+}
+
+int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
+                   const float* prev, const float* kernel4x4, float* out, rw_stream_t stream) {
+  if (!part || nparts < 1 || !bias || !out || (prev && !kernel4x4)) {
+    set_last_error("rw_rgb_combine: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return rgb_combine_launch(part, nparts, B, H, W, bias, prev, kernel4x4, out, stream);
 }
 
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,

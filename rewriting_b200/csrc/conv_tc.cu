@@ -222,6 +222,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
       }
 
+      // ---- fused epilogue -------------------------------------------------------------
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      const float* rw0 = p.rgb_w ? p.rgb_w + (static_cast<size_t>(b) * 3) * p.Cout : nullptr;
       if (valid) {
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
@@ -231,7 +234,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           t += nz;
           if (p.bias) t += __ldg(p.bias + o);
           if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
-          outp[static_cast<size_t>(o) * p.out_sc] = t;
+          acc[j] = t;
+          if (p.out != nullptr && p.out_mode == 0) outp[static_cast<size_t>(o) * p.out_sc] = t;
+          if (rw0) {
+            r0 = fmaf(__ldg(rw0 + o), t, r0);
+            r1 = fmaf(__ldg(rw0 + p.Cout + o), t, r1);
+            r2 = fmaf(__ldg(rw0 + 2 * p.Cout + o), t, r2);
+          }
+        }
+        if (rw0) {
+          const size_t hw = static_cast<size_t>(Hv) * Wv;
+          float* rp = p.rgb_part + ((static_cast<size_t>(mn % n_tiles) * p.B + b) * 3) * hw +
+                      static_cast<size_t>(yy) * Wv + xx;
+          rp[0] = r0;
+          rp[hw] = r1;
+          rp[2 * hw] = r2;
+        }
+      } else if (p.out_mode == 1 && prow < p.rows && scl) {
+        // channels-last raw rows are written for every row (pad rows are never read back)
+#pragma unroll
+        for (int j = 0; j < BN; ++j) acc[j] *= __ldg(scl + n0 + j);
+      }
+      if (p.out != nullptr && p.out_mode == 1 && prow < p.rows) {
+        float* dst = p.out + (static_cast<size_t>(ph) * p.rows + prow) * p.Cout + n0;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+      if (p.next_hi != nullptr && prow < p.rows) {
+        __nv_bfloat16* nh = static_cast<__nv_bfloat16*>(p.next_hi) +
+                            static_cast<size_t>(prow) * p.Cout + n0;
+        __nv_bfloat16* nl = static_cast<__nv_bfloat16*>(p.next_lo) +
+                            static_cast<size_t>(prow) * p.Cout + n0;
+        const float* ns = p.next_scale + static_cast<size_t>(valid ? b : 0) * p.Cout + n0;
+#pragma unroll
+        for (int j = 0; j < BN; j += 8) {
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float k0 = valid ? __ldg(ns + j + 2 * e) * acc[j + 2 * e] : 0.f;
+            const float k1 = valid ? __ldg(ns + j + 2 * e + 1) * acc[j + 2 * e + 1] : 0.f;
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(k0, k1);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(k0 - hf.x, k1 - hf.y);
+            hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(nh + j) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(nl + j) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
         }
       }
     }

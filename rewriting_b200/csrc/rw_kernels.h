@@ -24,6 +24,7 @@ struct ConvTcParams {
   int ph_Hv[4], ph_Wv[4];       // valid output extent inside the padded grid
   long long ph_out_ofs[4];      // element offset of this phase's output origin
   int Hp, Wp;        // padded grid of one image
+  int B;             // batch (only needed for the rgb partial layout)
   // epilogue
   const float* scale_bo;  // [B, Cout] per-sample per-channel scale (demod / style) or null
   const float* bias;      // [Cout] or null
@@ -31,8 +32,20 @@ struct ConvTcParams {
   long long noise_bstride;
   const float* noise_w;   // device scalar (read by the kernel: no host sync per layer)
   int act;                // 1 -> leaky_relu(0.2) * sqrt(2)
-  float* out;
+  float* out;             // may be null when only planes / rgb partials are wanted
   long long out_sb, out_sc, out_sy, out_sx;  // element strides: batch, channel, y, x
+  // out_mode 0: strided (NCHW-like) store at valid positions only
+  // out_mode 1: channels-last rows  out[(ph*rows + p)*Cout + o]  for every row p < rows
+  int out_mode;
+  // fused producer outputs (generation fast path): the NEXT layer's key planes
+  //   next_{hi,lo}[p][o] = split_bf16(next_scale[b,o] * y)   (zero at pad positions)
+  void* next_hi;
+  void* next_lo;
+  const float* next_scale;   // [B, Cout] style of the consuming layer
+  // and this layer's ToRGB partial sums over the tile's 128 output channels
+  //   rgb_part[nt][b][c][y*Wv+x] = sum_{o in tile} rgb_w[b][c][o] * y[b,o,y,x]
+  float* rgb_part;
+  const float* rgb_w;        // [B, 3, Cout] modulated 1x1 weights
 };
 
 int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
@@ -77,6 +90,12 @@ int demod_launch(const float* style, const float* wsq, int B, int Cout, int Cin,
 int blur_up_act_launch(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
                        const float* noise, long long noise_bstride, const float* noise_w,
                        const float* bias, int act, float* y, cudaStream_t stream);
+int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, const float* k4,
+                         const float* noise, long long noise_bstride, const float* noise_w,
+                         const float* bias, int act, const float* next_scale, void* next_hi,
+                         void* next_lo, float* y_out, cudaStream_t stream);
+int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
+                       const float* prev, const float* k4, float* out, cudaStream_t stream);
 int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
                      int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
                      int py1, float* out, int out_h, int out_w, cudaStream_t stream);

@@ -306,6 +306,155 @@ __global__ void add_noise_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------
+// blur_up_fused: generation fast path for an upsampling StyledConv.
+//   t_cl  [4 phases][rows_in][C] fp32 channels-last (conv_tc out_mode 1; phase = (ty&1)*2+(tx&1),
+//         row = (b*(H+1) + ty/2)*(W+1) + tx/2) — the conv_transpose output, demodulated
+//   v = act( FIR4x4(pad(t,1,1)) + noise_w*noise + bias )                       (as blur_up_act)
+//   -> next layer's key planes  split_bf16(next_scale[b,c] * v)  over the padded-flat grid of
+//      the OUTPUT resolution (pad row / column written as zeros), optional fp32 NCHW copy.
+// block: 64 channels x (8 x 16) outputs; thread = (pixel group, channel quad); float4 smem reads.
+// ---------------------------------------------------------------------------
+constexpr int BF_TY = 8, BF_TX = 16, BF_C = 64;
+constexpr int BF_PW = BF_TX + 3, BF_PH = BF_TY + 3;
+
+__global__ void __launch_bounds__(256)
+blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
+                     const float* __restrict__ k4, const float* __restrict__ noise,
+                     long long noise_bstride, const float* __restrict__ noise_w,
+                     const float* __restrict__ bias, int act,
+                     const float* __restrict__ next_scale, __nv_bfloat16* __restrict__ next_hi,
+                     __nv_bfloat16* __restrict__ next_lo, float* __restrict__ y_out) {
+  extern __shared__ float4 tile4[];      // [BF_PH*BF_PW][16 quads]
+  __shared__ float kf[16];
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int Hp_in = H + 1, Wp_in = W + 1;
+  const long long rows_in = static_cast<long long>(B) * Hp_in * Wp_in;
+  const int cblocks = C / BF_C;
+  const int b = blockIdx.z / cblocks;
+  const int c0 = (blockIdx.z - b * cblocks) * BF_C;
+  const int ox0 = blockIdx.x * BF_TX, oy0 = blockIdx.y * BF_TY;
+  const int tid = threadIdx.x;
+  if (tid < 16) kf[tid] = __ldg(k4 + 15 - tid);   // flipped kernel (upfirdn2d correlates)
+  for (int i = tid; i < BF_PH * BF_PW * 16; i += 256) {
+    const int qd = i & 15;
+    const int pos = i >> 4;
+    const int ly = pos / BF_PW, lx = pos - ly * BF_PW;
+    const int ty = oy0 + ly - 1, tx = ox0 + lx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ty >= 0 && ty <= Ho && tx >= 0 && tx <= Wo) {
+      const int ph = (ty & 1) * 2 + (tx & 1);
+      const long long row = (static_cast<long long>(b) * Hp_in + (ty >> 1)) * Wp_in + (tx >> 1);
+      v = __ldg(reinterpret_cast<const float4*>(t_cl + (ph * rows_in + row) * C + c0) + qd);
+    }
+    tile4[i] = v;
+  }
+  __syncthreads();
+  const int qd = tid & 15;
+  const int grp = tid >> 4;                 // 16 groups of 8 pixels
+  const int ly = grp >> 1;
+  const int lx0 = (grp & 1) * 8;
+  const int oy = oy0 + ly;
+  if (oy > Ho) return;
+  const int c = c0 + qd * 4;
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (next_scale) sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
+  const size_t out_row0 = (static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1);
+#pragma unroll 1
+  for (int px = 0; px < 8; ++px) {
+    const int lx = lx0 + px;
+    const int ox = ox0 + lx;
+    if (ox > Wo) break;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool real = (oy < Ho) && (ox < Wo);
+    if (real) {
+#pragma unroll
+      for (int fy = 0; fy < 4; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < 4; ++fx) {
+          const float4 tv = tile4[((ly + fy) * BF_PW + lx + fx) * 16 + qd];
+          const float kk = kf[fy * 4 + fx];
+          a.x = fmaf(tv.x, kk, a.x); a.y = fmaf(tv.y, kk, a.y);
+          a.z = fmaf(tv.z, kk, a.z); a.w = fmaf(tv.w, kk, a.w);
+        }
+      if (noise) {
+        const float nz = nw * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
+                                    static_cast<size_t>(oy) * Wo + ox);
+        a.x += nz; a.y += nz; a.z += nz; a.w += nz;
+      }
+      a.x += bs.x; a.y += bs.y; a.z += bs.z; a.w += bs.w;
+      if (act) {
+        a.x = (a.x > 0.f ? a.x : 0.2f * a.x) * 1.4142135623730951f;
+        a.y = (a.y > 0.f ? a.y : 0.2f * a.y) * 1.4142135623730951f;
+        a.z = (a.z > 0.f ? a.z : 0.2f * a.z) * 1.4142135623730951f;
+        a.w = (a.w > 0.f ? a.w : 0.2f * a.w) * 1.4142135623730951f;
+      }
+      if (y_out) {
+        const size_t hw = static_cast<size_t>(Ho) * Wo;
+        float* yp = y_out + (static_cast<size_t>(b) * C + c) * hw + static_cast<size_t>(oy) * Wo + ox;
+        yp[0] = a.x; yp[hw] = a.y; yp[2 * hw] = a.z; yp[3 * hw] = a.w;
+      }
+    }
+    if (next_hi) {
+      const float k0 = real ? sc.x * a.x : 0.f, k1 = real ? sc.y * a.y : 0.f;
+      const float k2 = real ? sc.z * a.z : 0.f, k3 = real ? sc.w * a.w : 0.f;
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(k0, k1), h23 = __floats2bfloat162_rn(k2, k3);
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(k0 - f01.x, k1 - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(k2 - f23.x, k3 - f23.y);
+      const size_t off = (out_row0 + ox) * C + c;
+      *reinterpret_cast<uint2*>(next_hi + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      *reinterpret_cast<uint2*>(next_lo + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// rgb_combine: out[b,c,y,x] = sum_nt part[nt][b][c][y][x] + bias[c] + Up2(prev)[b,c,y,x]
+// (ToRGBF's `+ bias + skip` with the skip's UpsampleO = upfirdn2d(up=2, pad=(2,1)) inline;
+//  models.py:435-447,639-655).  3-channel tensors: negligible traffic.
+// ---------------------------------------------------------------------------
+__global__ void rgb_combine_kernel(const float* __restrict__ part, int nparts, int B, int H, int W,
+                                   const float* __restrict__ bias, const float* __restrict__ prev,
+                                   const float* __restrict__ k4, float* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * 3 * H * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int bc = static_cast<int>(idx / (static_cast<long long>(W) * H));
+  float acc = 0.f;
+  for (int n = 0; n < nparts; ++n) acc += part[n * total + idx];
+  acc += __ldg(bias + bc % 3);
+  if (prev) {
+    const int h2 = H / 2, w2 = W / 2;
+    const float* src = prev + static_cast<size_t>(bc) * h2 * w2;
+    float u = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int uy = y + ky - 2;
+      if (uy < 0 || (uy & 1)) continue;
+      const int iy = uy >> 1;
+      if (iy >= h2) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ux = x + kx - 2;
+        if (ux < 0 || (ux & 1)) continue;
+        const int ix = ux >> 1;
+        if (ix >= w2) continue;
+        u = fmaf(__ldg(src + iy * w2 + ix), __ldg(k4 + (3 - ky) * 4 + (3 - kx)), u);
+      }
+    }
+    acc += u;
+  }
+  out[idx] = acc;
+}
+
 inline int grid_for(long long n, int threads, int cap = 148 * 16) {
   long long g = (n + threads - 1) / threads;
   if (g > cap) g = cap;
@@ -417,6 +566,45 @@ int add_noise_launch(const float* x, const float* noise, long long noise_bstride
   add_noise_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, noise, noise_bstride, noise_w, C,
                                                              HW, total, y);
   return check_cuda(cudaGetLastError(), "add_noise launch");
+}
+
+int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, const float* k4,
+                         const float* noise, long long noise_bstride, const float* noise_w,
+                         const float* bias, int act, const float* next_scale, void* next_hi,
+                         void* next_lo, float* y_out, cudaStream_t stream) {
+  if (C % BF_C != 0) {
+    set_last_error("blur_up_fused: C=%d must be a multiple of 64", C);
+    return RW_ERR_BAD_ARG;
+  }
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  const size_t smem = static_cast<size_t>(BF_PH) * BF_PW * 16 * sizeof(float4);
+  static bool attr = false;
+  if (!attr) {
+    int rc = check_cuda(cudaFuncSetAttribute(blur_up_fused_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)),
+                        "blur_up_fused smem attr");
+    if (rc) return rc;
+    attr = true;
+  }
+  const long long gz = static_cast<long long>(B) * (C / BF_C);
+  if (gz > 65535) {
+    set_last_error("blur_up_fused: grid.z %lld too large", gz);
+    return RW_ERR_BAD_ARG;
+  }
+  dim3 grid((Wo + 1 + BF_TX - 1) / BF_TX, (Ho + 1 + BF_TY - 1) / BF_TY, static_cast<unsigned>(gz));
+  blur_up_fused_kernel<<<grid, 256, smem, stream>>>(
+      t_cl, B, C, Hin, Win, k4, noise, noise_bstride, noise_w, bias, act, next_scale,
+      static_cast<__nv_bfloat16*>(next_hi), static_cast<__nv_bfloat16*>(next_lo), y_out);
+  return check_cuda(cudaGetLastError(), "blur_up_fused launch");
+}
+
+int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
+                       const float* prev, const float* k4, float* out, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * 3 * H * W;
+  rgb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      part, nparts, B, H, W, bias, prev, k4, out);
+  return check_cuda(cudaGetLastError(), "rgb_combine launch");
 }
 
 }  // namespace rw

@@ -1,0 +1,168 @@
+"""Generation fast path of an intact SeqStyleGAN2: producers write the consumer's operands.
+
+The layer-by-layer execution (`StyledConvSeq.forward`) has to hand an fp32 NCHW feature map to
+whatever comes next (a hook, a nethook slice, ToRGB, the next layer's prep), which costs three
+extra passes over every activation.  When the WHOLE generator runs unhooked and without
+autograd, nothing observes those tensors, so this module chains the kernels directly:
+
+    planes(L) --conv_tc--> epilogue { lrelu(..)·√2 ; x next style -> planes(L+1) ; ToRGB partial }
+    planes(L) --conv_tc(4 phases)--> t (channels-last) --blur_up_fused--> planes(L+1)
+    rgb partials --rgb_combine--> running image (+ bias + 2x-upsampled skip)
+
+The arithmetic per element is the same as the layer path (same kernels, same fp32 epilogue
+expressions), only the intermediate fp32 tensors are never materialised.  Also serves the
+rewriter's key collection: `upto_key_layer=N` stops in front of `layerN`'s convolution and returns
+its key planes, which are exactly the operands of the second-moment GEMM.
+
+Reference semantics: SeqStyleGAN2.forward, utils/stylegan2/models.py:92-141.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi, ops
+from .ops import _p, _stream
+
+
+def _layer_list(model):
+    """[(layer number, StyledConvSeq, latent index, ToRGBF or None, rgb latent index)] in order,
+    or None if the module tree is not the pristine SeqStyleGAN2 layout."""
+    from .utils.stylegan2 import models as sg2
+    names = list(model._modules.keys())
+    expect = ['bag_in', 'style', 'latents', 'noises', 'input', 'layer2', 'to_rgb1']
+    n = 3
+    for k in range(1, model.log_size - 1):
+        expect += ['up_rgb%d' % k, 'layer%d' % n, 'layer%d' % (n + 1), 'to_rgb%d' % (k + 1)]
+        n += 2
+    expect.append('output')
+    if names != expect:
+        return None
+    out = []
+    for name in names:
+        if not name.startswith('layer'):
+            continue
+        num = int(name[5:])
+        seq = model._modules[name]
+        kids = list(seq._modules.items())
+        if len(kids) != 2 or not isinstance(kids[0][1], sg2.PickLatent):
+            return None
+        sconv = kids[1][1]
+        if not isinstance(sconv, sg2.StyledConvSeq):
+            return None
+        mc = sconv._modules.get('mconv')
+        if not isinstance(mc, sg2.ModulatedConv2dSeq):
+            return None
+        want = ['modulation', 'adain', 'dconv'] + (['blur'] if mc.upsample else [])
+        if list(mc._modules.keys()) != want or list(sconv._modules.keys()) != ['mconv', 'noise', 'activate']:
+            return None
+        if mc.dconv.kernel_size != 3 or not mc.dconv.demodulate:
+            return None
+        rgb = None
+        rgb_lat = None
+        if num % 2 == 0:
+            rseq = model._modules['to_rgb%d' % (num // 2)]
+            rk = list(rseq._modules.items())
+            if len(rk) != 2 or not isinstance(rk[1][1], sg2.ToRGBF):
+                return None
+            rgb, rgb_lat = rk[1][1], rk[0][1].index
+        out.append((num, sconv, kids[0][1].index, rgb, rgb_lat))
+    return out
+
+
+def eligible(model, z):
+    from .utils.stylegan2 import models as sg2
+    if not isinstance(z, torch.Tensor) or z.dim() != 2 or not z.is_cuda or z.dtype != torch.float32:
+        return False
+    if model.bag_input or model.bag_output or model.mconv != 'seq':
+        return False
+    if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in model.parameters())):
+        return False
+    if sg2._is_hooked(model):
+        return False
+    return _layer_list(model) is not None
+
+
+def forward(model, z, upto_key_layer=None):
+    """image [B,3,size,size] (or KeyPlanes of `layer<upto_key_layer>`'s key)."""
+    from .utils.stylegan2 import models as sg2
+    layers = _layer_list(model)
+    if layers is None:
+        raise _cabi.RwError('fastpath: the module tree is not a pristine SeqStyleGAN2')
+    dev = z.device
+    d = model.latents(model.style(model.bag_in(z)))
+    latent = d.latent                                    # [B, n_latent, 512]
+    B = z.shape[0]
+    stream = _stream()
+
+    # all styles up front (they only depend on the latent)
+    styles = {}
+    for num, sconv, lat, rgb, rgb_lat in layers:
+        mod = sconv.mconv.modulation
+        styles[num] = sg2.EqualLinear.forward(mod, latent[:, lat]).contiguous()
+
+    x0 = model.input.input
+    H = W = x0.shape[2]
+    first = layers[0]
+    planes, _ = ops.prep_keys(x0.repeat(B, 1, 1, 1), styles[first[0]])
+    if upto_key_layer == first[0]:
+        return planes
+    image = None
+    for idx, (num, sconv, lat, rgb, rgb_lat) in enumerate(layers):
+        if upto_key_layer == num:
+            return planes
+        mc = sconv.mconv
+        dconv = mc.dconv
+        Cin, Cout = dconv.in_channel, dconv.out_channel
+        w_hi, w_lo, wsq = ops.weight_planes(dconv.weight, 'fwd')
+        dm = ops.demod_factors(styles[num], wsq)
+        nxt = layers[idx + 1] if idx + 1 < len(layers) else None
+        next_scale = styles[nxt[0]] if nxt is not None else None
+        nw = sconv.noise.weight.detach()
+        bias = sconv.activate.bias.detach()
+        if mc.upsample:
+            rows = B * (H + 1) * (W + 1)
+            t_cl = torch.empty((4, rows, Cout), dtype=torch.float32, device=dev)
+            _cabi.call('rw_modconv_up_fwd_cl', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
+                       _p(dm), B, Cin, Cout, H, W, _p(t_cl), stream)
+            Ho, Wo = 2 * H, 2 * W
+            noise = ops.noise_table(B, Ho * Wo, dev)
+            rows_o = B * (Ho + 1) * (Wo + 1)
+            nh = torch.empty((rows_o, Cout), dtype=torch.bfloat16, device=dev)
+            nl = torch.empty_like(nh)
+            _cabi.call('rw_blur_up_fused', _p(t_cl), B, Cout, H, W, _p(mc.blur.kernel), _p(noise),
+                       noise.stride(0), _p(nw), _p(bias), 1, _p(next_scale), _p(nh), _p(nl), None,
+                       stream)
+            H, W = Ho, Wo
+            planes = ops.KeyPlanes(nh, nl, B, Cout, H, W)
+        else:
+            noise = ops.noise_table(B, H * W, dev)
+            rows = B * (H + 1) * (W + 1)
+            nh = nl = None
+            if nxt is not None:
+                nh = torch.empty((rows, Cout), dtype=torch.bfloat16, device=dev)
+                nl = torch.empty_like(nh)
+            rgb_w = rgb_part = None
+            ntile = Cout // 128
+            if rgb is not None:
+                s_rgb = rgb.conv.modulation(latent[:, rgb_lat])                # [B, Cout]
+                w3 = rgb.conv.weight.detach().reshape(3, Cout) * (1.0 / math.sqrt(Cout))
+                rgb_w = (w3[None, :, :] * s_rgb[:, None, :]).contiguous()       # [B,3,Cout]
+                rgb_part = torch.empty((ntile, B, 3, H, W), dtype=torch.float32, device=dev)
+            _cabi.call('rw_modconv_fwd_fused', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
+                       _p(dm), _p(noise), noise.stride(0), _p(nw), _p(bias), 1, B, Cin, Cout, H, W,
+                       None, _p(next_scale), _p(nh), _p(nl), _p(rgb_w), _p(rgb_part), stream)
+            if rgb is not None:
+                out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+                up_k = None
+                if image is not None:
+                    up_k = model._modules['up_rgb%d' % (num // 2 - 1)].kernel
+                _cabi.call('rw_rgb_combine', _p(rgb_part), ntile, B, H, W,
+                           _p(rgb.bias.detach().reshape(3).contiguous()), _p(image), _p(up_k),
+                           _p(out), stream)
+                image = out
+            if nxt is not None:
+                planes = ops.KeyPlanes(nh, nl, B, Cout, H, W)
+    if upto_key_layer is not None:
+        raise ValueError('layer%s not found' % upto_key_layer)
+    return image

@@ -43,6 +43,8 @@ from ..utils.stylegan2 import models as sg2
 (all_obs, all_weight, all_CinvK, all_kCinvK, e_val, e_vec, kbasis, row_dirs, q) = (None,) * 9
 
 FUSED_CHUNK = 64     # iterations per fused launch when a callback wants per-step losses
+import re as _re
+_DCONV_RE = _re.compile(r'^layer(\d+)\.(?:sconv|conv)\.mconv\.dconv$')
 
 
 class ProgressiveGanRewriter(object):
@@ -134,8 +136,16 @@ class ProgressiveGanRewriter(object):
 
     # ---------------------------------------------------------------------------- statistics
     def _key_planes(self, zbatch):
-        """context forward -> bf16 hi/lo planes of the keys (rows = pixels, cols = channels)."""
-        acts = self.context_acts(self.context_model(zbatch.to(self.device)))
+        """context forward -> bf16 hi/lo planes of the keys (rows = pixels, cols = channels).
+        When the key is the input of `layerN...dconv` of an intact SeqStyleGAN2, the fused
+        generation pipeline is run up to that convolution and its operand planes ARE the keys
+        (no fp32 key tensor, no permute)."""
+        from .. import fastpath
+        z = zbatch.to(self.device)
+        m = _DCONV_RE.match(self.firstlayer)
+        if m and isinstance(self.model, sg2.SeqStyleGAN2) and fastpath.eligible(self.model, z):
+            return fastpath.forward(self.model, z, upto_key_layer=int(m.group(1)))
+        acts = self.context_acts(self.context_model(z))
         planes, _ = ops.prep_keys(acts, None)
         return planes
 

@@ -558,6 +558,15 @@ class SeqStyleGAN2(nn.Sequential):
             seq.append(('output', ReturnOutput()))
         super().__init__(OrderedDict(seq))
 
+    def forward(self, x):
+        """Whole-generator calls on an unhooked model without autograd take the fused fast path
+        (`rewriting_b200.fastpath`: producers write the next layer's operands, no fp32 feature
+        maps in between); anything else runs child by child like nn.Sequential."""
+        from ... import fastpath
+        if fastpath.eligible(self, x):
+            return fastpath.forward(self, x)
+        return nn.Sequential.forward(self, x)
+
     def bag_from_z(self, z):
         return InputLatent()(z)
 

@@ -216,6 +216,38 @@ def test_generator_pixels_vs_golden_and_oracle(cuda_model, seeded_sd, z40, golde
     assert (one[0] - pix[0]).abs().max().item() < 1e-3
 
 
+def test_generation_fast_path_equals_layer_path(cuda_model, z40):
+    """model(z) (fused producers, no fp32 feature maps) == child-by-child execution, and the
+    fast path's key planes == planes of the context model's key tensor."""
+    from rewriting_b200 import fastpath, ops
+    from rewriting_b200.utils import nethook
+    z = z40[:3].cuda()
+    with torch.no_grad():
+        assert fastpath.eligible(cuda_model, z)
+        fast = cuda_model(z)
+        slow = torch.nn.Sequential.forward(cuda_model, z)
+    assert fast.shape == slow.shape == (3, 3, 256, 256)
+    assert (fast - slow).abs().max().item() < 1e-4
+    for layer in (8, 9, 4):
+        ctx = nethook.subsequence(cuda_model, upto_layer='layer%d.sconv.mconv.dconv' % layer,
+                                  share_weights=True)
+        with torch.no_grad():
+            kp = fastpath.forward(cuda_model, z, upto_key_layer=layer)
+            ref_planes, _ = ops.prep_keys(ctx(z).fmap, None)
+        assert (kp.B, kp.C, kp.H, kp.W) == (ref_planes.B, ref_planes.C, ref_planes.H, ref_planes.W)
+        a = kp.hi.float() + kp.lo.float()
+        b = ref_planes.hi.float() + ref_planes.lo.float()
+        assert (a - b).abs().max().item() < 1e-4 * max(1.0, b.abs().max().item())
+    # not eligible with autograd on or when hooked -> falls back transparently
+    zz = z.clone().requires_grad_(True)
+    assert not fastpath.eligible(cuda_model, zz)
+    with nethook.InstrumentedModel(cuda_model) as inst, torch.no_grad():
+        inst.retain_layer('layer4', detach=False)
+        assert not fastpath.eligible(cuda_model, z)
+        hooked = inst(z)
+    assert (hooked - slow).abs().max().item() < 1e-4
+
+
 def test_fused_layers_equal_leaf_by_leaf_execution(cuda_model, z40):
     """The nethook-split execution (context | target | rendering, leaves one by one) must give
     the same image as the fused whole-layer path."""
