@@ -59,6 +59,15 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+// tile -> (phase, mn).  Phases have very different tap counts (4/2/2/1 for a stride-2
+// conv_transpose); with a static round-robin over a grid that is a multiple of nphase every CTA
+// would always draw the same phase, so the phase is rotated by the CTA's iteration index.
+__device__ __forceinline__ void decode_tile(int tile, int nphase, int& ph, int& mn) {
+  mn = tile / nphase;
+  ph = tile - mn * nphase;
+  if (nphase > 1 && (gridDim.x % nphase) == 0) ph = (ph + tile / static_cast<int>(gridDim.x)) % nphase;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
@@ -109,8 +118,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ph = tile % p.nphase;
-        const int mn = tile / p.nphase;
+        int ph, mn;
+        decode_tile(tile, p.nphase, ph, mn);
         const int n0 = (mn % n_tiles) * BN;
         const int m0 = (mn / n_tiles) * BM;
         for (int t = 0; t < p.ph_ntaps[ph]; ++t) {
@@ -137,7 +146,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int num_kb = p.ph_ntaps[tile % p.nphase] * kb_per_tap;
+      int ph_m, mn_m;
+      decode_tile(tile, p.nphase, ph_m, mn_m);
+      const int num_kb = p.ph_ntaps[ph_m] * kb_per_tap;
       if (lane == 0) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
           const int as = chunk % kNumAcc;
@@ -177,8 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int img = p.Hp * p.Wp;
     uint32_t chunk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ph = tile % p.nphase;
-      const int mn = tile / p.nphase;
+      int ph, mn;
+      decode_tile(tile, p.nphase, ph, mn);
       const int num_kb = p.ph_ntaps[ph] * kb_per_tap;
       const int Hv = p.ph_Hv[ph], Wv = p.ph_Wv[ph];
       const int n0 = (mn % n_tiles) * BN;
