@@ -48,7 +48,11 @@ struct ConvSmem {
   static constexpr int kABytes = BM * BK * 2;   // one plane
   static constexpr int kBBytes = BN * BK * 2;   // one plane
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per-epilogue-warp transpose scratch: 32 rows x (128 B + 16 B pad)
+  static constexpr int kScratchRow = 144;
+  static constexpr int kScratchBytes = 4 * 32 * kScratchRow;
+  static constexpr int kTotal = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ +
+                                256 /*barriers*/;
 };
 
 struct Barriers {
@@ -78,7 +82,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   using S = ConvSmem<BN>;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * S::kStageBytes);
+  uint8_t* scratch_base = smem + kStages * S::kStageBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(scratch_base + S::kScratchBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,33 +271,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int j = 0; j < BN; ++j) acc[j] *= __ldg(scl + n0 + j);
       }
-      if (p.out != nullptr && p.out_mode == 1 && prow < p.rows) {
-        float* dst = p.out + (static_cast<size_t>(ph) * p.rows + prow) * p.Cout + n0;
+      // Row-per-lane registers -> global through a warp-private smem transpose, so that every
+      // store instruction covers whole 128-byte lines (4 rows x 128 B) instead of 32 rows x 16 B.
+      uint8_t* scr = scratch_base + (warp - 2) * 32 * S::kScratchRow;
+      const int rr0 = lane >> 3;        // row within a group of 4
+      const int c16 = lane & 7;         // 16-byte column slot
+      if (p.out != nullptr && p.out_mode == 1) {
 #pragma unroll
-        for (int j = 0; j < BN; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(scr + lane * S::kScratchRow + j4 * 16) = make_float4(
+                acc[c0 + 4 * j4], acc[c0 + 4 * j4 + 1], acc[c0 + 4 * j4 + 2], acc[c0 + 4 * j4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rr0;
+            const int grow = m0 + q * 32 + rr;
+            const float4 v = *reinterpret_cast<const float4*>(scr + rr * S::kScratchRow + c16 * 16);
+            if (grow < p.rows)
+              *reinterpret_cast<float4*>(p.out + (static_cast<size_t>(ph) * p.rows + grow) * p.Cout +
+                                         n0 + c0 + c16 * 4) = v;
+          }
+          __syncwarp();
+        }
       }
-      if (p.next_hi != nullptr && prow < p.rows) {
-        __nv_bfloat16* nh = static_cast<__nv_bfloat16*>(p.next_hi) +
-                            static_cast<size_t>(prow) * p.Cout + n0;
-        __nv_bfloat16* nl = static_cast<__nv_bfloat16*>(p.next_lo) +
-                            static_cast<size_t>(prow) * p.Cout + n0;
+      if (p.next_hi != nullptr) {
         const float* ns = p.next_scale + static_cast<size_t>(valid ? b : 0) * p.Cout + n0;
 #pragma unroll
-        for (int j = 0; j < BN; j += 8) {
-          uint32_t hp[4], lp[4];
+        for (int half = 0; half < BN / 64; ++half) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float k0 = valid ? __ldg(ns + j + 2 * e) * acc[j + 2 * e] : 0.f;
-            const float k1 = valid ? __ldg(ns + j + 2 * e + 1) * acc[j + 2 * e + 1] : 0.f;
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(k0, k1);
-            const float2 hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(k0 - hf.x, k1 - hf.y);
-            hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
-            lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          for (int plane = 0; plane < 2; ++plane) {
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = half * 64 + j8 * 8 + 2 * e;
+                const float k0 = valid ? __ldg(ns + j) * acc[j] : 0.f;
+                const float k1 = valid ? __ldg(ns + j + 1) * acc[j + 1] : 0.f;
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(k0, k1);
+                if (plane == 0) {
+                  w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                } else {
+                  const float2 hf = __bfloat1622float2(hh);
+                  const __nv_bfloat162 ll = __floats2bfloat162_rn(k0 - hf.x, k1 - hf.y);
+                  w[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+              }
+              *reinterpret_cast<uint4*>(scr + lane * S::kScratchRow + j8 * 16) =
+                  make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            __syncwarp();
+            __nv_bfloat16* dstp = static_cast<__nv_bfloat16*>(plane == 0 ? p.next_hi : p.next_lo);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rr0;
+              const int grow = m0 + q * 32 + rr;
+              const uint4 v = *reinterpret_cast<const uint4*>(scr + rr * S::kScratchRow + c16 * 16);
+              if (grow < p.rows)
+                *reinterpret_cast<uint4*>(dstp + static_cast<size_t>(grow) * p.Cout + n0 + half * 64 +
+                                          c16 * 8) = v;
+            }
+            __syncwarp();
           }
-          *reinterpret_cast<uint4*>(nh + j) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(nl + j) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
         }
       }
     }
