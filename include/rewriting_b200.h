@@ -108,6 +108,11 @@ int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const fl
                      const float* noise, long long noise_bstride, const float* noise_w,
                      const float* bias, int act, const float* next_scale, void* next_hi,
                      void* next_lo, float* y_out, rw_stream_t stream);
+/* all modulation linears in one launch: out_l[b,c] = latent[b,lat_l,:] . (W_l[c,:]*scale) + bias_l[c]
+ * (HOST arrays of n device pointers / ints; n <= 32) */
+int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int n,
+              const float* const* w, const float* const* bias, float* const* out, const int* lat,
+              const int* chans, rw_stream_t stream);
 int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
                    const float* prev, const float* kernel4x4, float* out, rw_stream_t stream);
 /* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */

@@ -331,6 +331,16 @@ int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const fl
                               act, next_scale, next_hi, next_lo, y_out, stream);
 }
 
+int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int n,
+              const float* const* w, const float* const* bias, float* const* out, const int* lat,
+              const int* chans, rw_stream_t stream) {
+  if (!latent || !w || !bias || !out || !lat || !chans || B < 1) {
+    set_last_error("rw_styles: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return styles_launch(latent, B, n_latent, K, scale, n, w, bias, out, lat, chans, stream);
+}
+
 int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
                    const float* prev, const float* kernel4x4, float* out, rw_stream_t stream) {
   if (!part || nparts < 1 || !bias || !out || (prev && !kernel4x4)) {

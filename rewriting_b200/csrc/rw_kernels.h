@@ -96,6 +96,9 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
                          void* next_lo, float* y_out, cudaStream_t stream);
 int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
                        const float* prev, const float* k4, float* out, cudaStream_t stream);
+int styles_launch(const float* latent, int B, int n_latent, int K, float scale, int n,
+                  const float* const* w, const float* const* bias, float* const* out,
+                  const int* lat, const int* chans, cudaStream_t stream);
 int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
                      int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
                      int py1, float* out, int out_h, int out_w, cudaStream_t stream);

@@ -363,44 +363,57 @@ blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
   if (next_scale) sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
   const size_t out_row0 = (static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1);
-#pragma unroll 1
+
+  // 8 consecutive outputs of one row: slide over 11 input columns per filter row, so every
+  // smem value is read once (44 LDS.128 instead of 128) — the kernel is smem-bound otherwise.
+  float4 a[8];
+#pragma unroll
+  for (int px = 0; px < 8; ++px) a[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int fy = 0; fy < 4; ++fy) {
+    float4 tv[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) tv[i] = tile4[((ly + fy) * BF_PW + lx0 + i) * 16 + qd];
+#pragma unroll
+    for (int fx = 0; fx < 4; ++fx) {
+      const float kk = kf[fy * 4 + fx];
+#pragma unroll
+      for (int px = 0; px < 8; ++px) {
+        a[px].x = fmaf(tv[px + fx].x, kk, a[px].x);
+        a[px].y = fmaf(tv[px + fx].y, kk, a[px].y);
+        a[px].z = fmaf(tv[px + fx].z, kk, a[px].z);
+        a[px].w = fmaf(tv[px + fx].w, kk, a[px].w);
+      }
+    }
+  }
+#pragma unroll
   for (int px = 0; px < 8; ++px) {
-    const int lx = lx0 + px;
-    const int ox = ox0 + lx;
+    const int ox = ox0 + lx0 + px;
     if (ox > Wo) break;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = a[px];
     const bool real = (oy < Ho) && (ox < Wo);
     if (real) {
-#pragma unroll
-      for (int fy = 0; fy < 4; ++fy)
-#pragma unroll
-        for (int fx = 0; fx < 4; ++fx) {
-          const float4 tv = tile4[((ly + fy) * BF_PW + lx + fx) * 16 + qd];
-          const float kk = kf[fy * 4 + fx];
-          a.x = fmaf(tv.x, kk, a.x); a.y = fmaf(tv.y, kk, a.y);
-          a.z = fmaf(tv.z, kk, a.z); a.w = fmaf(tv.w, kk, a.w);
-        }
       if (noise) {
         const float nz = nw * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
                                     static_cast<size_t>(oy) * Wo + ox);
-        a.x += nz; a.y += nz; a.z += nz; a.w += nz;
+        v.x += nz; v.y += nz; v.z += nz; v.w += nz;
       }
-      a.x += bs.x; a.y += bs.y; a.z += bs.z; a.w += bs.w;
+      v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
       if (act) {
-        a.x = (a.x > 0.f ? a.x : 0.2f * a.x) * 1.4142135623730951f;
-        a.y = (a.y > 0.f ? a.y : 0.2f * a.y) * 1.4142135623730951f;
-        a.z = (a.z > 0.f ? a.z : 0.2f * a.z) * 1.4142135623730951f;
-        a.w = (a.w > 0.f ? a.w : 0.2f * a.w) * 1.4142135623730951f;
+        v.x = (v.x > 0.f ? v.x : 0.2f * v.x) * 1.4142135623730951f;
+        v.y = (v.y > 0.f ? v.y : 0.2f * v.y) * 1.4142135623730951f;
+        v.z = (v.z > 0.f ? v.z : 0.2f * v.z) * 1.4142135623730951f;
+        v.w = (v.w > 0.f ? v.w : 0.2f * v.w) * 1.4142135623730951f;
       }
       if (y_out) {
         const size_t hw = static_cast<size_t>(Ho) * Wo;
         float* yp = y_out + (static_cast<size_t>(b) * C + c) * hw + static_cast<size_t>(oy) * Wo + ox;
-        yp[0] = a.x; yp[hw] = a.y; yp[2 * hw] = a.z; yp[3 * hw] = a.w;
+        yp[0] = v.x; yp[hw] = v.y; yp[2 * hw] = v.z; yp[3 * hw] = v.w;
       }
     }
     if (next_hi) {
-      const float k0 = real ? sc.x * a.x : 0.f, k1 = real ? sc.y * a.y : 0.f;
-      const float k2 = real ? sc.z * a.z : 0.f, k3 = real ? sc.w * a.w : 0.f;
+      const float k0 = real ? sc.x * v.x : 0.f, k1 = real ? sc.y * v.y : 0.f;
+      const float k2 = real ? sc.z * v.z : 0.f, k3 = real ? sc.w * v.w : 0.f;
       const __nv_bfloat162 h01 = __floats2bfloat162_rn(k0, k1), h23 = __floats2bfloat162_rn(k2, k3);
       const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
       const __nv_bfloat162 l01 = __floats2bfloat162_rn(k0 - f01.x, k1 - f01.y);
@@ -453,6 +466,58 @@ __global__ void rgb_combine_kernel(const float* __restrict__ part, int nparts, i
     acc += u;
   }
   out[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// styles: every modulation EqualLinear of the generator in ONE launch.
+//   out_l[b, c] = sum_k latent[b, lat_l, k] * (W_l[c, k] * scale) + bias_l[c]
+// (EqualLinearS / ModulatedConv2d.modulation, models.py:487-511 with lr_mul = 1,
+//  activation = None).  The reference issues one tiny sgemm per layer (20 per forward).
+// one warp per (layer, output channel); the weight row is read once, coalesced.
+// ---------------------------------------------------------------------------
+struct StyleJobs {
+  const float* w[32];
+  const float* bias[32];
+  float* out[32];
+  int lat[32];
+  int chans[32];
+  int first_warp[33];
+  int n;
+};
+
+__global__ void __launch_bounds__(256)
+styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, float scale,
+              const StyleJobs jobs) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= jobs.first_warp[jobs.n]) return;
+  int l = 0;
+  while (gw >= jobs.first_warp[l + 1]) ++l;
+  const int c = gw - jobs.first_warp[l];
+  const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
+  const float bv = __ldg(jobs.bias[l] + c);
+  const float* x0 = latent + static_cast<size_t>(jobs.lat[l]) * K;
+  float* out = jobs.out[l];
+  const int C = jobs.chans[l];
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wrow + k) * scale;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (b0 + i < B)
+          acc[i] = fmaf(__ldg(x0 + static_cast<size_t>(b0 + i) * n_latent * K + k), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = acc[i];
+#pragma unroll
+      for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0 && b0 + i < B) out[static_cast<size_t>(b0 + i) * C + c] = a + bv;
+    }
+  }
 }
 
 inline int grid_for(long long n, int threads, int cap = 148 * 16) {
@@ -605,6 +670,32 @@ int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const
   rgb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       part, nparts, B, H, W, bias, prev, k4, out);
   return check_cuda(cudaGetLastError(), "rgb_combine launch");
+}
+
+int styles_launch(const float* latent, int B, int n_latent, int K, float scale, int n,
+                  const float* const* w, const float* const* bias, float* const* out,
+                  const int* lat, const int* chans, cudaStream_t stream) {
+  if (n < 1 || n > 32) {
+    set_last_error("styles: %d layers (max 32)", n);
+    return RW_ERR_BAD_ARG;
+  }
+  StyleJobs jobs;
+  jobs.n = n;
+  int warps = 0;
+  for (int i = 0; i < n; ++i) {
+    jobs.w[i] = w[i];
+    jobs.bias[i] = bias[i];
+    jobs.out[i] = out[i];
+    jobs.lat[i] = lat[i];
+    jobs.chans[i] = chans[i];
+    jobs.first_warp[i] = warps;
+    warps += chans[i];
+  }
+  jobs.first_warp[n] = warps;
+  const int threads = 256;
+  const int blocks = (warps * 32 + threads - 1) / threads;
+  styles_kernel<<<blocks, threads, 0, stream>>>(latent, B, n_latent, K, scale, jobs);
+  return check_cuda(cudaGetLastError(), "styles launch");
 }
 
 }  // namespace rw
