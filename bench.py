@@ -351,11 +351,12 @@ def main():
     # ---- extras: covariance samples/s and rewrite-loop its/s --------------------------------
     extra = {}
     if not args.no_extra:
-        ctx = nethook.subsequence(model, upto_layer='layer8.sconv.mconv.dconv', share_weights=True)
+        from rewriting_b200 import fastpath
         with torch.no_grad():
             def cov_step(zb, r2m):
-                acts = ctx(zb).fmap
-                planes, _ = ops.prep_keys(acts, None)
+                # what SeqStyleGanRewriter.collect_2nd_moment does per batch: generator up to
+                # layer 8's conv, whose operand planes are the keys, then the col-GEMM
+                planes = fastpath.forward(model, zb, upto_key_layer=8)
                 r2m.add_planes(planes.hi, planes.lo, planes.B * planes.H * planes.W)
             r2m = runningstats.RunningSecondMoment()
             for i in range(W):

@@ -485,20 +485,28 @@ struct StyleJobs {
   int n;
 };
 
+// block = (layer, 8-channel group): the B latent rows of that layer are staged in smem once,
+// each of the 8 warps owns one output channel and reads its weight row once.
 __global__ void __launch_bounds__(256)
 styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, float scale,
               const StyleJobs jobs) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= jobs.first_warp[jobs.n]) return;
+  extern __shared__ float xs[];            // [B][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int l = 0;
-  while (gw >= jobs.first_warp[l + 1]) ++l;
-  const int c = gw - jobs.first_warp[l];
+  const int blk = blockIdx.x;
+  while (blk >= jobs.first_warp[l + 1]) ++l;          // first_warp holds BLOCK offsets here
+  const int c = (blk - jobs.first_warp[l]) * 8 + warp;
+  const float* x0 = latent + static_cast<size_t>(jobs.lat[l]) * K;
+  for (int i = threadIdx.x; i < B * K; i += 256) {
+    const int b = i / K, k = i - b * K;
+    xs[i] = __ldg(x0 + static_cast<size_t>(b) * n_latent * K + k);
+  }
+  __syncthreads();
+  const int C = jobs.chans[l];
+  if (c >= C) return;
   const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
   const float bv = __ldg(jobs.bias[l] + c);
-  const float* x0 = latent + static_cast<size_t>(jobs.lat[l]) * K;
   float* out = jobs.out[l];
-  const int C = jobs.chans[l];
   for (int b0 = 0; b0 < B; b0 += 8) {
     float acc[8];
 #pragma unroll
@@ -507,8 +515,7 @@ styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, floa
       const float wv = __ldg(wrow + k) * scale;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (b0 + i < B)
-          acc[i] = fmaf(__ldg(x0 + static_cast<size_t>(b0 + i) * n_latent * K + k), wv, acc[i]);
+        if (b0 + i < B) acc[i] = fmaf(xs[(b0 + i) * K + k], wv, acc[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -689,12 +696,23 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     jobs.lat[i] = lat[i];
     jobs.chans[i] = chans[i];
     jobs.first_warp[i] = warps;
-    warps += chans[i];
+    warps += (chans[i] + 7) / 8;          // blocks of 8 channels
   }
   jobs.first_warp[n] = warps;
-  const int threads = 256;
-  const int blocks = (warps * 32 + threads - 1) / threads;
-  styles_kernel<<<blocks, threads, 0, stream>>>(latent, B, n_latent, K, scale, jobs);
+  const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_last_error("styles: B*K too large for shared memory");
+    return RW_ERR_UNSUPPORTED;
+  }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    int rc = check_cuda(cudaFuncSetAttribute(styles_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)), "styles smem attr");
+    if (rc) return rc;
+    attr = smem;
+  }
+  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
 }
 
