@@ -378,11 +378,12 @@ def main():
                                    'ms_per_step': ms_cov / K,
                                    'collective': 'one all_reduce(sum) of mom2[512,512] fp32 + '
                                                  'count after the last batch'}
-        if rank == 0:
-            try:
-                extra['insert_loop'] = bench_insert(model, z_dev, device)
-            except Exception as e:  # noqa: BLE001
-                extra['insert_loop'] = {'error': '%s: %s' % (type(e).__name__, e)}
+        # every rank builds a rewriter: its constructor collects C collectively (sharded z +
+        # one all-reduce) when torch.distributed is initialised; the edit itself is "replicas only"
+        try:
+            extra['insert_loop'] = bench_insert(model, z_dev, device)
+        except Exception as e:  # noqa: BLE001
+            extra['insert_loop'] = {'error': '%s: %s' % (type(e).__name__, e)}
 
     if rank == 0:
         peaks = measured_peaks()
