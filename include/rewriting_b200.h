@@ -144,6 +144,20 @@ int rw_conv_wgrad(const void* g_hi, const void* g_lo, const void* kp_hi, const v
                   long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
                   size_t workspace_bytes, rw_stream_t stream);
 
+/* backward of the upsampling layer: gradient phase planes [rows][4*Cout] (rw_prep_phase_keys from the
+ * gradient wrt the conv_transpose output [B,Cout,2H+1,2W+1], times demod), then
+ *   dk[b,i,y,x] = sum_{o,u,v} g[b,o,2y+u,2x+v] * scale*W[o,i,u,v]      (rw_modconv_up_dgrad, weights
+ *                 as [Cin][tap][Cout] planes, taps NOT flipped)
+ *   dW[o][tap][i] = sum_p G_phase(tap)[p + shift(tap), o] * K[p, i]     (rw_conv_up_wgrad) */
+int rw_prep_phase_keys(const float* g, const float* scale_bc, int B, int C, int H, int W,
+                       void* hi, void* lo, rw_stream_t stream);
+int rw_modconv_up_dgrad(const void* gph_hi, const void* gph_lo, const void* wt_hi,
+                        const void* wt_lo, const float* scale_bi, int B, int Cin, int Cout, int H,
+                        int W, float* dk, rw_stream_t stream);
+int rw_conv_up_wgrad(const void* gph_hi, const void* gph_lo, const void* kp_hi, const void* kp_lo,
+                     long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
+                     size_t workspace_bytes, rw_stream_t stream);
+
 /* ---- rank-r edit ---- */
 /* out = base + sign * P_d(w);  P_d(w)[o,:,t] = sum_r (w[o,:,t] . d_r) d_r;  base may be NULL */
 int rw_project_rank(const float* w, const float* base, const float* d, int rank, int Cout,

@@ -70,6 +70,11 @@ SIGNATURES = {
     'rw_second_moment_accum': (c_int, [c_p, c_p, c_ll, c_int, c_p, c_p, c_sz, c_p]),
     'rw_conv_wgrad': (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_int, c_int, c_p, c_p, c_sz,
                               c_p]),
+    'rw_prep_phase_keys': (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
+    'rw_modconv_up_dgrad': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_p, c_p]),
+    'rw_conv_up_wgrad': (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_int, c_int, c_p, c_p, c_sz,
+                                 c_p]),
     'rw_project_rank': (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_p, c_p]),
     'rw_insert_loop': (c_int, [ctypes.POINTER(InsertArgs), c_p]),
     'rw_debug_rowgemm': (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
@@ -114,7 +119,7 @@ def check(rc, what):
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
 LAUNCHES_PER_CALL = {
-    'rw_second_moment_accum': 2, 'rw_conv_wgrad': 2,
+    'rw_second_moment_accum': 2, 'rw_conv_wgrad': 2, 'rw_conv_up_wgrad': 2,
     'rw_debug_colgemm': 2,
 }
 launch_count = 0

@@ -478,6 +478,78 @@ int rw_conv_wgrad(const void* g_hi, const void* g_lo, const void* kp_hi, const v
                                 /*accumulate=*/0, /*mirror_upper=*/0, stream);
 }
 
+int rw_prep_phase_keys(const float* g, const float* scale_bc, int B, int C, int H, int W,
+                       void* hi, void* lo, rw_stream_t stream) {
+  if (!g || !hi || !lo || B < 1) {
+    set_last_error("rw_prep_phase_keys: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return prep_phase_keys_launch(g, scale_bc, B, C, H, W, hi, lo, stream);
+}
+
+// tap (u,v) of the stride-2 conv_transpose reads gradient phase (u&1, v&1) at row shift
+// (u>>1)*(W+1) + (v>>1) of the INPUT-resolution padded grid.
+int rw_modconv_up_dgrad(const void* gph_hi, const void* gph_lo, const void* wt_hi,
+                        const void* wt_lo, const float* scale_bi, int B, int Cin, int Cout, int H,
+                        int W, float* dk, rw_stream_t stream) {
+  if (!gph_hi || !gph_lo || !wt_hi || !wt_lo || !dk || B < 1) {
+    set_last_error("rw_modconv_up_dgrad: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  // GEMM: M = input pixels, K = 9 taps x Cout (gradient channels), N = Cin
+  ConvTcParams p;
+  int rc = fill_conv3x3(p, B, /*Cin(K)=*/Cout, /*Cout(N)=*/Cin, H, W);
+  if (rc) return rc;
+  p.a_cols = 4 * Cout;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      const int t = u * 3 + v;
+      p.ph_shift[0][t] = (u >> 1) * p.Wp + (v >> 1);
+      p.ph_acol[0][t] = ((u & 1) * 2 + (v & 1)) * Cout;
+      p.ph_kofs[0][t] = t * Cout;
+    }
+  p.scale_bo = scale_bi;
+  p.out = dk;
+  return conv_tc_launch(p, gph_hi, gph_lo, wt_hi, wt_lo, 9 * Cout, stream);
+}
+
+int rw_conv_up_wgrad(const void* gph_hi, const void* gph_lo, const void* kp_hi, const void* kp_lo,
+                     long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
+                     size_t workspace_bytes, rw_stream_t stream) {
+  if (!gph_hi || !gph_lo || !kp_hi || !kp_lo || !dw_toi || !workspace || rows <= 0 ||
+      rows > 0x7fffffffLL) {
+    set_last_error("rw_conv_up_wgrad: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  GramTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = static_cast<int>(rows);
+  p.rows_a = p.rows_b = static_cast<int>(rows);
+  p.Cm = Cout;
+  p.Cn = Cin;
+  p.a_cols = 4 * Cout;
+  p.ntaps = 9;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      const int t = u * 3 + v;
+      p.tap_shift_a[t] = (u >> 1) * Wp + (v >> 1);
+      p.tap_acol[t] = ((u & 1) * 2 + (v & 1)) * Cout;
+      p.tap_col_ofs[t] = t * Cin;
+    }
+  p.splits = gram_splits((Cout / 128) * (Cin / 128), rows, 9);
+  p.ldp = 9LL * Cin;
+  p.partial = static_cast<float*>(workspace);
+  const size_t need = static_cast<size_t>(p.splits) * Cout * 9 * Cin * sizeof(float);
+  if (workspace_bytes < need) {
+    set_last_error("rw_conv_up_wgrad: workspace %zu < %zu bytes", workspace_bytes, need);
+    return RW_ERR_BAD_ARG;
+  }
+  int rc = gram_tc_launch(p, gph_hi, gph_lo, kp_hi, kp_lo, stream);
+  if (rc) return rc;
+  return reduce_partials_launch(p.partial, p.splits, Cout, 9 * Cin, p.ldp, dw_toi, 9LL * Cin, 0, 0,
+                                stream);
+}
+
 int rw_project_rank(const float* w, const float* base, const float* d, int rank, int Cout,
                     int Cin, int taps, float sign, float* out, rw_stream_t stream) {
   if (!w || !d || !out) {

@@ -130,12 +130,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         for (int t = 0; t < p.ph_ntaps[ph]; ++t) {
           const int arow = m0 + p.ph_shift[ph][t];
           const int wcol = p.ph_kofs[ph][t];
+          const int acol = p.ph_acol[ph][t];
           for (int kb = 0; kb < kb_per_tap; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             uint8_t* st = smem + stage * S::kStageBytes;
             mbar_expect_tx(&bars->full[stage], S::kStageBytes);
-            tma_load_2d(st, &map_a_hi, &bars->full[stage], kb * BK, arow);
-            tma_load_2d(st + S::kABytes, &map_a_lo, &bars->full[stage], kb * BK, arow);
+            tma_load_2d(st, &map_a_hi, &bars->full[stage], acol + kb * BK, arow);
+            tma_load_2d(st + S::kABytes, &map_a_lo, &bars->full[stage], acol + kb * BK, arow);
             tma_load_2d(st + 2 * S::kABytes, &map_w_hi, &bars->full[stage], wcol + kb * BK, n0);
             tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_w_lo, &bars->full[stage],
                         wcol + kb * BK, n0);
@@ -365,8 +366,9 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
     }
   CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, p.Cin, p.rows, (uint64_t)p.Cin * 2, BK, BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, p.Cin, p.rows, (uint64_t)p.Cin * 2, BK, BM))) return rc;
+  const int a_cols = p.a_cols > 0 ? p.a_cols : p.Cin;
+  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
   if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))
     return rc;
   if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))

@@ -77,6 +77,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int n0 = nt * TN;
   const int tap = blockIdx.z;
   const int shift_b = p.shift_b + p.tap_shift_b[tap];
+  const int shift_a = p.shift_a + p.tap_shift_a[tap];
+  const int acol = p.tap_acol[tap];
   const int col_ofs = p.tap_col_ofs[tap];
 
   const int total_rb = (p.rows + RB - 1) / RB;
@@ -116,13 +118,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         mbar_wait(&bars->empty[stage], phase ^ 1u);
         uint8_t* st = smem + stage * kStageBytes;
         mbar_expect_tx(&bars->full[stage], kStageBytes);
-        const int ra = rb * RB + p.shift_a;
+        const int ra = rb * RB + shift_a;
         const int rbb = rb * RB + shift_b;
 #pragma unroll
         for (int j = 0; j < TM / 64; ++j) {
-          tma_load_2d(st + j * kBlockBytes, &map_a_hi, &bars->full[stage], m0 + j * 64, ra);
+          tma_load_2d(st + j * kBlockBytes, &map_a_hi, &bars->full[stage], acol + m0 + j * 64, ra);
           tma_load_2d(st + kPlaneBytes + j * kBlockBytes, &map_a_lo, &bars->full[stage],
-                      m0 + j * 64, ra);
+                      acol + m0 + j * 64, ra);
           tma_load_2d(st + 2 * kPlaneBytes + j * kBlockBytes, &map_b_hi, &bars->full[stage],
                       n0 + j * 64, rbb);
           tma_load_2d(st + 3 * kPlaneBytes + j * kBlockBytes, &map_b_lo, &bars->full[stage],
@@ -247,14 +249,17 @@ int gram_tc_launch(const GramTcParams& p, const void* a_hi, const void* a_lo, co
   }
   // rows r >= p.rows must contribute zero: clip the A operand's row extent at the
   // contraction range so the TMA zero-fills past it (B may then hold anything).
-  long long a_extent = static_cast<long long>(p.rows) + p.shift_a;
+  int max_sa = p.tap_shift_a[0];
+  for (int t = 1; t < p.ntaps; ++t) max_sa = p.tap_shift_a[t] > max_sa ? p.tap_shift_a[t] : max_sa;
+  long long a_extent = static_cast<long long>(p.rows) + p.shift_a + max_sa;
   if (a_extent > p.rows_a) a_extent = p.rows_a;
   if (a_extent < 1) a_extent = 1;
+  const int a_cols = p.a_cols > 0 ? p.a_cols : p.Cm;
   const long long b_extent = p.rows_b;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, p.Cm, a_extent, (uint64_t)p.Cm * 2, 64, RB))) return rc;
-  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, p.Cm, a_extent, (uint64_t)p.Cm * 2, 64, RB))) return rc;
+  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, a_cols, a_extent, (uint64_t)a_cols * 2, 64, RB))) return rc;
+  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, a_cols, a_extent, (uint64_t)a_cols * 2, 64, RB))) return rc;
   if ((rc = make_tmap_2d_bf16(&mb_hi, b_hi, p.Cn, b_extent, (uint64_t)p.Cn * 2, 64, RB))) return rc;
   if ((rc = make_tmap_2d_bf16(&mb_lo, b_lo, p.Cn, b_extent, (uint64_t)p.Cn * 2, 64, RB))) return rc;
 

@@ -21,6 +21,9 @@ struct ConvTcParams {
   int ph_ntaps[4];
   int ph_shift[4][9];   // row shift applied to the A operand for this tap
   int ph_kofs[4][9];    // column offset of this tap inside the weight matrix
+  int ph_acol[4][9];    // column offset of this tap inside the A planes (0 unless A holds
+                        // several channel-concatenated tensors, e.g. the 4 gradient phases)
+  int a_cols;           // total columns of the A planes (0 -> Cin)
   int ph_Hv[4], ph_Wv[4];       // valid output extent inside the padded grid
   long long ph_out_ofs[4];      // element offset of this phase's output origin
   int Hp, Wp;        // padded grid of one image
@@ -60,6 +63,9 @@ struct GramTcParams {
   int Cm, Cn;          // channels of A (-> M) and B (-> N)
   int shift_a, shift_b;
   int ntaps;              // >= 1; grid.z
+  int tap_shift_a[9];     // extra row shift of the A operand per tap
+  int tap_acol[9];        // column offset inside the A planes per tap
+  int a_cols;             // total columns of the A planes (0 -> Cm)
   int tap_shift_b[9];     // extra row shift of the B operand per tap
   int tap_col_ofs[9];     // column offset of this tap's block inside a partial row
   int splits;          // row-range splits (partials reduced deterministically afterwards)
@@ -80,6 +86,8 @@ int reduce_partials_launch(const float* partial, int splits, int M, int N, long 
 // ---------------------------------------------------------------------------
 // SIMT kernels (simt.cu)
 // ---------------------------------------------------------------------------
+int prep_phase_keys_launch(const float* g, const float* scale_bc, int B, int C, int H, int W,
+                           void* hi, void* lo, cudaStream_t stream);
 int prep_keys_launch(const float* x, const float* style, int B, int C, int H, int W, void* kp_hi,
                      void* kp_lo, float* k_out, cudaStream_t stream);
 int split_rows_launch(const float* a, long long n, void* hi, void* lo, cudaStream_t stream);

@@ -67,6 +67,61 @@ prep_keys_kernel(const float* __restrict__ x, const float* __restrict__ style, i
 }
 
 // ---------------------------------------------------------------------------
+// prep_phase_keys: gradient planes of a stride-2 conv_transpose output.
+//   g [B,C,2H+1,2W+1] fp32 (gradient wrt the conv_transpose output), scale_bc [B,C] (demod)
+//   -> planes [rows = B*(H+1)*(W+1)][4*C]: column block ph = a*2+b holds
+//      scale * g[b, c, 2m+a, 2n+b]  at row (b, m, n)   (zero where 2m+a > 2H or 2n+b > 2W)
+// so that dgrad / wgrad of the polyphase conv are again row-shift GEMMs over ONE matrix.
+// grid: (ceil(Hp*Wp/32), C/64, B*4), block 256 — same smem transpose as prep_keys.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_phase_keys_kernel(const float* __restrict__ g, const float* __restrict__ scale, int C, int H,
+                       int W, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[64][33];
+  const int Hp = H + 1, Wp = W + 1, Ht = 2 * H + 1, Wt = 2 * W + 1;
+  const int img = Hp * Wp;
+  const int p0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64;
+  const int b = blockIdx.z >> 2, ph = blockIdx.z & 3;
+  const int pa = ph >> 1, pb = ph & 1;
+  const int t = threadIdx.x;
+  {
+    const int pl = t & 31;
+    const int p = p0 + pl;
+    const int m = p / Wp, n = p - m * Wp;
+    const int ty = 2 * m + pa, tx = 2 * n + pb;
+    const bool valid = (p < img) && (ty < Ht) && (tx < Wt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cl = (t >> 5) + 8 * i;
+      float v = 0.f;
+      if (valid) {
+        const size_t gi = ((static_cast<size_t>(b) * C + c0 + cl) * Ht + ty) * Wt + tx;
+        const float s = scale ? __ldg(scale + static_cast<size_t>(b) * C + c0 + cl) : 1.f;
+        v = s * __ldg(g + gi);
+      }
+      tile[cl][pl] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int pl = t >> 3;
+    const int cg = (t & 7) * 8;
+    const int p = p0 + pl;
+    if (p < img) {
+      __align__(16) __nv_bfloat16 h[8];
+      __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(tile[cg + j][pl], h[j], l[j]);
+      const size_t row = static_cast<size_t>(b) * img + p;
+      const size_t off = row * (4 * static_cast<size_t>(C)) + static_cast<size_t>(ph) * C + c0 + cg;
+      *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // split_rows: fp32 -> bf16 hi/lo planes, same shape (generic RunningSecondMoment
 // input [N, C], runningstats.py:1086)
 // ---------------------------------------------------------------------------
@@ -714,6 +769,20 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
   }
   styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
+}
+
+int prep_phase_keys_launch(const float* g, const float* scale_bc, int B, int C, int H, int W,
+                           void* hi, void* lo, cudaStream_t stream) {
+  if (C % 64 != 0) {
+    set_last_error("prep_phase_keys: C=%d must be a multiple of 64", C);
+    return RW_ERR_BAD_ARG;
+  }
+  const int img = (H + 1) * (W + 1);
+  dim3 grid((img + 31) / 32, C / 64, B * 4);
+  prep_phase_keys_kernel<<<grid, 256, 0, stream>>>(g, scale_bc, C, H, W,
+                                                   static_cast<__nv_bfloat16*>(hi),
+                                                   static_cast<__nv_bfloat16*>(lo));
+  return check_cuda(cudaGetLastError(), "prep_phase_keys launch");
 }
 
 }  // namespace rw

@@ -123,6 +123,10 @@ def weight_planes(weight, kind='fwd'):
         wsq = None
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 1, 1, _p(hi), _p(lo), None,
                    _stream())
+    elif kind == 'dgrad_up':   # [Cin][tap][Cout] (conv_transpose: taps are not flipped)
+        wsq = None
+        _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 1, 0, _p(hi), _p(lo), None,
+                   _stream())
     else:
         raise ValueError(kind)
     val = (hi, lo, wsq)
@@ -320,11 +324,12 @@ class StyledConvFunction(torch.autograd.Function):
         if nw is None:
             with_noise = False
         b = _f32c(bias.detach()) if (with_act and bias is not None) else None
+        t_up = None
         if upsample:
-            t = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)
+            t_up = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)
             Ho, Wo = 2 * H, 2 * W
             noise = noise_table(B, Ho * Wo, x.device) if with_noise else None
-            y = blur_up_act(t, blur_kernel, noise, nw, b, with_act)
+            y = blur_up_act(t_up, blur_kernel, noise, nw, b, with_act)
         else:
             noise = noise_table(B, H * W, x.device) if with_noise else None
             y = conv3x3_planes(planes, w_hi, w_lo, Cout, dm, noise, nw, b, with_act)
@@ -332,21 +337,23 @@ class StyledConvFunction(torch.autograd.Function):
         ctx.cfg = (upsample, demodulate, with_noise, with_act, pre_modulated)
         ctx.blur_kernel = blur_kernel
         ctx.wholder = wholder
-        ctx.planes = planes if not upsample else None
+        needs_bwd = any(ctx.needs_input_grad)
+        ctx.planes = planes if needs_bwd else None
+        ctx.t_up = t_up if needs_bwd else None      # conv_transpose output * demod (up layers)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, style, weight, noise_weight, bias, y, dm = ctx.saved_tensors
         upsample, demodulate, with_noise, with_act, pre_modulated = ctx.cfg
-        if upsample:
-            raise _cabi.RwError('StyledConvFunction.backward: upsample layers are forward-only in '
-                                'this round (use an even target layer)')
+        if ctx.planes is None:
+            raise _cabi.RwError('StyledConvFunction.backward: forward ran without autograd state')
         gy = _f32c(gy)
         B, Cin, H, W = x.shape
         Cout = weight.shape[-4]
         sc = 1.0 / math.sqrt(Cin * 9)
         w4 = weight.detach().reshape(Cout, Cin, 3, 3)
+        Ho, Wo = (2 * H, 2 * W) if upsample else (H, W)
         # through the activation: gate on the sign of the saved output
         if with_act:
             g_pre = fused_bias_act_raw(gy, None, y, 3, 1, LRELU_SLOPE, LRELU_GAIN)
@@ -354,42 +361,67 @@ class StyledConvFunction(torch.autograd.Function):
             g_pre = gy
         g_bias = g_pre.sum(dim=(0, 2, 3)) if (with_act and bias is not None) else None
         g_nw = None
-        noise = noise_table(B, H * W, x.device) if with_noise else None
+        noise = noise_table(B, Ho * Wo, x.device) if with_noise else None
         if with_noise and noise_weight is not None:
             g_nw = (g_pre.sum(dim=1).reshape(B, -1) * noise).sum().reshape(1)
-        # gradient planes of g_t = g_pre * demod
-        g_planes, _ = prep_keys(g_pre, dm)
-        # dgrad: dk = conv(g_t, flip(W)^T)
-        wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad')
-        dk = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)
+        k_planes = ctx.planes
+        if upsample:
+            # adjoint of the blur (upfirdn2d with the flipped kernel and the adjoint padding)
+            kflip = torch.flip(ctx.blur_kernel, [0, 1]).contiguous()
+            g_t = upfirdn2d_raw(g_pre.reshape(B * Cout, Ho, Wo, 1), kflip, 1, 1, 1, 1, 2, 2, 2, 2)
+            g_t = g_t.view(B, Cout, 2 * H + 1, 2 * W + 1)
+            rows = B * (H + 1) * (W + 1)
+            gph_hi = torch.empty((rows, 4 * Cout), dtype=torch.bfloat16, device=x.device)
+            gph_lo = torch.empty_like(gph_hi)
+            _cabi.call('rw_prep_phase_keys', _p(g_t), _p(dm), B, Cout, H, W, _p(gph_hi),
+                       _p(gph_lo), _stream())
+            wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad_up')
+            dk = torch.empty((B, Cin, H, W), dtype=torch.float32, device=x.device)
+            _cabi.call('rw_modconv_up_dgrad', _p(gph_hi), _p(gph_lo), _p(wd_hi), _p(wd_lo), None,
+                       B, Cin, Cout, H, W, _p(dk), _stream())
+            lib = _cabi.load()
+            ws = _workspace(lib.rw_gram_workspace_bytes(Cout, Cin, rows, 9), x.device)
+            dwt = torch.empty((Cout, 9, Cin), dtype=torch.float32, device=x.device)
+            _cabi.call('rw_conv_up_wgrad', _p(gph_hi), _p(gph_lo), _p(k_planes.hi),
+                       _p(k_planes.lo), rows, Cout, Cin, W + 1, _p(dwt), _p(ws), ws.numel() * 4,
+                       _stream())
+            Gd = (g_t * ctx.t_up).sum(dim=(2, 3)) if demodulate else None   # = dL/d(demod) * demod
+        else:
+            # gradient planes of g_t = g_pre * demod
+            g_planes, _ = prep_keys(g_pre, dm)
+            # dgrad: dk = conv(g_t, flip(W)^T)
+            wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad')
+            dk = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)
+            dwt = conv_wgrad_planes(g_planes, k_planes)            # [Cout, 9, Cin]
+            Gd = None
+            if demodulate:
+                # recover t*demod = pre-activation - noise - bias from the saved output
+                if with_act:
+                    pre = torch.where(y > 0, y / LRELU_GAIN, y / (LRELU_SLOPE * LRELU_GAIN))
+                    if bias is not None:
+                        pre = pre - bias.detach().view(1, -1, 1, 1)
+                else:
+                    pre = y
+                if with_noise and noise_weight is not None:
+                    pre = pre - noise_weight.detach() * noise.view(B, 1, H, W)
+                Gd = (g_pre * pre).sum(dim=(2, 3))
         if pre_modulated:
             gx, g_style = dk, None
-            k_planes = ctx.planes
         else:
             gx = dk * style[:, :, None, None]
             g_style = (dk * x).sum(dim=(2, 3))
-            k_planes = ctx.planes
-        # wgrad
-        dwt = conv_wgrad_planes(g_planes, k_planes)            # [Cout, 9, Cin]
         gW = (sc * dwt).permute(0, 2, 1).reshape(Cout, Cin, 3, 3)
         if demodulate:
-            # recover t*demod = pre-activation - noise - bias from the saved output
-            if with_act:
-                pre = torch.where(y > 0, y / LRELU_GAIN, y / (LRELU_SLOPE * LRELU_GAIN))
-                if bias is not None:
-                    pre = pre - bias.detach().view(1, -1, 1, 1)
-            else:
-                pre = y
-            if with_noise and noise_weight is not None:
-                pre = pre - noise_weight.detach() * noise.view(B, 1, H, W)
-            Gd = (g_pre * pre).sum(dim=(2, 3))                 # = dL/d(demod) * demod
-            coef = Gd * dm * dm                                # dL/ddemod * demod^3 / demod ...
+            coef = Gd * dm * dm
             s2 = style * style
             # d demod/dW = -demod^3 * sc^2 * W * s^2 ;  dL/ddemod = Gd/demod
             gW = gW - (sc * sc) * w4 * torch.matmul(coef.t(), s2)[:, :, None, None]
             if g_style is not None:
                 wsq = ctx.wholder.planes('fwd')[2]
                 g_style = g_style - style * torch.matmul(coef, wsq)
+            elif pre_modulated and style.requires_grad:
+                wsq = ctx.wholder.planes('fwd')[2]
+                g_style = -style * torch.matmul(coef, wsq)
         gW = gW.reshape(weight.shape)
         return gx, g_style, gW, g_nw, g_bias, None, None, None, None, None, None, None
 

@@ -120,6 +120,37 @@ def test_styled_conv_backward_vs_oracle_autograd():
         assert err < 3e-4 * max(1.0, want.abs().max().item()), (name, err)
 
 
+def test_styled_conv_upsample_backward_vs_oracle_autograd():
+    from rewriting_b200 import ops
+    torch.manual_seed(7)
+    B, Cin, Cout, H, W = 2, 128, 128, 5, 6
+    x = torch.randn(B, Cin, H, W, requires_grad=True)
+    style = (torch.randn(B, Cin) * 0.5 + 1.0).requires_grad_(True)
+    weight = torch.randn(1, Cout, Cin, 3, 3, requires_grad=True)
+    nw = torch.tensor([0.37], requires_grad=True)
+    bias = torch.randn(Cout, requires_grad=True)
+    kern = orc.make_kernel([1, 3, 3, 1]) * 4
+    gy = torch.randn(B, Cout, 2 * H, 2 * W)
+    t = orc.demod_conv(style[:, :, None, None] * x, style, weight, upsample=True)
+    tb = orc.upfirdn2d(t, kern, pad=(1, 1))
+    n = orc.noise_table(B, 4 * H * W).view(B, 1, 2 * H, 2 * W)
+    ref = orc.fused_leaky_relu(tb + nw * n, bias)
+    ref.backward(gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    sc = style.detach().cuda().requires_grad_(True)
+    wc = torch.nn.Parameter(weight.detach().cuda())
+    nc = torch.nn.Parameter(nw.detach().cuda())
+    bc = torch.nn.Parameter(bias.detach().cuda())
+    y = ops.styled_conv(xc, sc, wc, nc, bc, upsample=True, blur_kernel=kern.cuda(), demodulate=True)
+    assert (y.detach().cpu() - ref.detach()).abs().max().item() < 2e-4 * ref.abs().max().item()
+    y.backward(gy.cuda())
+    for name, got, want in [('x', xc.grad, x.grad), ('style', sc.grad, style.grad),
+                            ('weight', wc.grad, weight.grad), ('noise_w', nc.grad, nw.grad),
+                            ('bias', bc.grad, bias.grad)]:
+        err = (got.cpu() - want).abs().max().item()
+        assert err < 3e-4 * max(1.0, want.abs().max().item()), (name, err)
+
+
 def test_operator_level_ops_vs_oracle():
     from rewriting_b200.utils.stylegan2 import op
     torch.manual_seed(4)
