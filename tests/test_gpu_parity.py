@@ -399,3 +399,81 @@ def test_fused_insert_equals_autograd_insert_and_oracle(cuda_model, z40, golden)
     assert (diff > 1e-3).float().mean().item() < 5e-2
     rel = ((results['autograd'] - W_orc).norm() / (W_orc - W0).norm()).item()
     assert rel < 5e-2, rel
+
+
+# ------------------------------------------------------------------------------------------
+# edit variants on the same kernels
+# ------------------------------------------------------------------------------------------
+def _goal_bags(gw, golden):
+    bag = gw.context_model(gw.get_z(0))
+    gin = type(bag)(bag, fmap=torch.from_numpy(golden['goal_in_fmap']).cuda(),
+                    style=torch.from_numpy(golden['goal_in_style']).cuda())
+    gout = type(bag)(bag, fmap=torch.from_numpy(golden['goal_out_fmap']).cuda())
+    return gin, gout
+
+
+def test_insert_variants_rank2_gradient_projection_and_tiny_target(cuda_model, z40, golden):
+    from rewriting_b200.rewrite import ganrewrite
+    zds = torch.utils.data.TensorDataset(z40[:10])
+    sd = cuda_model.state_dict()
+    nw = sd['layer8.sconv.noise.weight'].cpu()
+    bias = sd['layer8.sconv.activate.bias'].cpu()
+    torch.manual_seed(11)
+    q, _ = torch.linalg.qr(torch.randn(512, 2))
+    d2 = q.t().contiguous()
+    k = torch.from_numpy(golden['goal_in_fmap'])
+    st = torch.from_numpy(golden['goal_in_style'])
+    tgt = torch.from_numpy(golden['goal_out_fmap'])
+    # rank 2, with and without gradient projection
+    for lrg in (False, True):
+        gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8, low_rank_gradient=lrg)
+        gin, gout = _goal_bags(gw, golden)
+        W0 = gw.target_weights().detach().clone().cpu()
+        gw.insert(gin, gout, d2.cuda(), niter=12, piter=5, lr=0.05)
+        W = gw.target_weights().detach().cpu()
+        W_orc = orc.insert_loop(W0, k, st, tgt, nw, bias, d2, 12, piter=5, lr=0.05,
+                                low_rank_gradient=lrg)
+        assert (W - W_orc).abs().max().item() < 1e-4, lrg
+        s = torch.linalg.svdvals((W - W0)[0].permute(0, 2, 3, 1).reshape(-1, 512).double())
+        assert float(s[2] / s[0]) < 1e-5                      # rank <= 2
+    # SeqTiny: the target model is the dconv leaf alone (no noise / activation)
+    gw = ganrewrite.SeqTinyStyleGanRewriter(cuda_model, zds, 8)
+    gin, gout = _goal_bags(gw, golden)
+    assert gw._fused_plan(gin, gout, d2.cuda()) is not None
+    W0 = gw.target_weights().detach().clone().cpu()
+    gw.insert(gin, gout, d2[:1].cuda(), niter=12, piter=5, lr=0.05)
+    W_orc = orc.insert_loop(W0, k, st, tgt, nw, bias, d2[:1], 12, piter=5, lr=0.05,
+                            with_noise_act=False)
+    assert (gw.target_weights().detach().cpu() - W_orc).abs().max().item() < 1e-4
+
+
+def test_zero_linear_insert_and_erase_run_on_the_kernels(cuda_model, z40, golden, edit_request):
+    from rewriting_b200.rewrite import ganrewrite
+    zds = torch.utils.data.TensorDataset(z40)
+    d = torch.from_numpy(golden['d']).cuda()
+    # zero(): the component of W along d becomes `amount` times that of an all-ones weight
+    gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8)
+    W0 = gw.target_weights().detach().clone()
+    gw.zero(d, amount=0.25)
+    W = gw.target_weights().detach()
+    want = W0 - orc.projected_conv(W0.cpu(), d.cpu()).cuda() + \
+        0.25 * orc.projected_conv(torch.ones_like(W0).cpu(), d.cpu()).cuda()
+    assert (W - want).abs().max().item() < 2e-5
+    # linear_insert: optimises Lambda; the edit stays rank one and the loss goes down
+    gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8, use_linear_insert=True)
+    gin, gout = _goal_bags(gw, golden)
+    W0 = gw.target_weights().detach().clone()
+    losses = []
+    gw.insert(gin, gout, d, niter=15, lr=0.05, update_callback=lambda it, l: losses.append(float(l)))
+    dW = (gw.target_weights().detach() - W0)[0].permute(0, 2, 3, 1).reshape(-1, 512).double().cpu()
+    s = torch.linalg.svdvals(dW)
+    assert float(s[1] / s[0]) < 1e-5 and float(s[0]) > 0
+    assert losses[-1] < losses[0]
+    assert isinstance(gw.target_weights(), torch.nn.Parameter)          # parameter restored
+    # apply_erase: end to end on the request (normdissect units + insert); weights must move
+    gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8)
+    W0 = gw.target_weights().detach().clone()
+    gw.apply_erase(dict(paste=edit_request['paste'], key=edit_request['key']), rank=1, drank=30,
+                   niter=11, piter=10)
+    moved = (gw.target_weights().detach() - W0).abs().max().item()
+    assert 1e-3 < moved < 1.0 and torch.isfinite(gw.target_weights()).all()
