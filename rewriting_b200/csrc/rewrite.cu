@@ -26,6 +26,10 @@ constexpr int kMaxW = 16;      // crop width handled by the register tile
 constexpr int kMaxRank = 32;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+// the insert loop runs one output channel per CTA, 4 warps, 4 CTAs per SM: all 512 channels
+// of a layer are resident at once (592 CTA slots) and their latency-bound phases interleave
+constexpr int kLoopThreads = 128;
+constexpr int kLoopWarps = kLoopThreads / 32;
 
 // out[o,i,t] = base[o,i,t] + sign * sum_r d[r,i] * (sum_j W[o,j,t] d[r,j])
 // one CTA per output channel o; row o of W is contiguous (Cin*taps floats).
@@ -67,7 +71,7 @@ struct LoopSmem {
   // dynamic: W[Cin*9] | t[P] | gd[P] | red[...] ...
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kLoopThreads, 4)
 insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
   extern __shared__ float sm[];
   const int Cin = p.Cin, h = p.h, w = p.w, B = p.B;
@@ -82,8 +86,8 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
   float* sc_b = lam + kMaxRank * 9;   // [B] demod, [B] coeff, loss, misc (64 floats)
   float* demodS = sc_b;
   float* coefS = sc_b + 16;
-  float* lossS = sc_b + 32;       // [kWarps]
-  float* GS = sc_b + 40;          // [kWarps*? ] per-warp partial G[b] -> B<=... stored [kWarps][B<=2]?
+  float* lossS = sc_b + 32;       // [kLoopWarps]
+  float* GS = sc_b + 40;          // [kLoopWarps*? ] per-warp partial G[b] -> B<=... stored [kLoopWarps][B<=2]?
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float sc = rsqrtf(static_cast<float>(Cin * 9));
@@ -94,7 +98,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
     float* Wg = p.W + static_cast<size_t>(o) * nW;
     float* mg = p.m + static_cast<size_t>(o) * nW;
     float* vg = p.v + static_cast<size_t>(o) * nW;
-    for (int i = threadIdx.x; i < nW; i += kThreads) Ws[i] = Wg[i];
+    for (int i = threadIdx.x; i < nW; i += kLoopThreads) Ws[i] = Wg[i];
     __syncthreads();
 
     for (int step = 0; step < p.nsteps; ++step) {
@@ -119,7 +123,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         if (lane == 0) demodS[b] = rsqrtf(acc + 1e-8f);
       }
       // ---- forward conv on the crop: warp <-> row units (b, y), lane <-> channel
-      for (int u = warp; u < B * h; u += kWarps) {
+      for (int u = warp; u < B * h; u += kLoopWarps) {
         const int b = u / h, y = u - b * h;
         float acc[kMaxW];
 #pragma unroll
@@ -156,7 +160,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       // ---- loss / output gradient, one thread per pixel; block-reduce loss and G[b]
       float lsum = 0.f;
       float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int q = threadIdx.x; q < P; q += kThreads) {
+      for (int q = threadIdx.x; q < P; q += kLoopThreads) {
         const int b = q / (h * w);
         const int pp = q - b * h * w;
         const float t = tS[q];
@@ -192,12 +196,12 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       __syncthreads();
       if (threadIdx.x == 0) {
         float l = 0.f;
-        for (int wv = 0; wv < kWarps; ++wv) l += lossS[wv];
+        for (int wv = 0; wv < kLoopWarps; ++wv) l += lossS[wv];
         p.loss_out[static_cast<size_t>(step) * p.Cout + o] = l;
       }
       if (threadIdx.x < B) {
         float G = 0.f;
-        for (int wv = 0; wv < kWarps; ++wv) G += GS[wv * 4 + threadIdx.x];
+        for (int wv = 0; wv < kLoopWarps; ++wv) G += GS[wv * 4 + threadIdx.x];
         const float dm = demodS[threadIdx.x];
         coefS[threadIdx.x] = G * dm * dm * dm;
       }
@@ -213,7 +217,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       const float one_m_b1 = 1.0f - p.beta1;
       const float one_m_b2 = 1.0f - p.beta2;
 
-      for (int j = warp; j < nch; j += kWarps) {
+      for (int j = warp; j < nch; j += kLoopWarps) {
         const int i = lane + 32 * j;
         float acc[9];
 #pragma unroll
@@ -255,7 +259,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       __syncthreads();
       // ---- optional gradient projection onto span(d)   (ganrewrite.py:285-286)
       if (p.project_gradient) {
-        for (int rt = warp; rt < p.rank * 9; rt += kWarps) {
+        for (int rt = warp; rt < p.rank * 9; rt += kLoopWarps) {
           const int r = rt / 9, t = rt - r * 9;
           float a = 0.f;
           for (int i = lane; i < Cin; i += 32) a = fmaf(dWS[i * 9 + t], __ldg(p.d + r * Cin + i), a);
@@ -264,7 +268,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
           if (lane == 0) lam[rt] = a;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < nW; e += kThreads) {
+        for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
           const int i = e / 9, t = e - i * 9;
           float pr = 0.f;
           for (int r = 0; r < p.rank; ++r) pr = fmaf(lam[r * 9 + t], __ldg(p.d + r * Cin + i), pr);
@@ -273,7 +277,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         __syncthreads();
       }
       // ---- Adam (torch.optim.Adam, amsgrad=False, weight_decay=0)
-      for (int e = threadIdx.x; e < nW; e += kThreads) {
+      for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
         const float g = dWS[e];
         float mm = mg[e], vv = vg[e];
         mm = mm + (g - mm) * one_m_b1;                 // exp_avg.lerp_(grad, 1-beta1)
@@ -286,7 +290,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       __syncthreads();
       // ---- periodic projection  W <- W_ortho + P_d(W)   (ganrewrite.py:291-294)
       if (p.w_ortho != nullptr && (it % p.piter == 0 || it == p.niter_total - 1)) {
-        for (int rt = warp; rt < p.rank * 9; rt += kWarps) {
+        for (int rt = warp; rt < p.rank * 9; rt += kLoopWarps) {
           const int r = rt / 9, t = rt - r * 9;
           float a = 0.f;
           for (int i = lane; i < Cin; i += 32) a = fmaf(Ws[i * 9 + t], __ldg(p.d + r * Cin + i), a);
@@ -296,7 +300,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         }
         __syncthreads();
         const float* wo = p.w_ortho + static_cast<size_t>(o) * nW;
-        for (int e = threadIdx.x; e < nW; e += kThreads) {
+        for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
           const int i = e / 9, t = e - i * 9;
           float pr = 0.f;
           for (int r = 0; r < p.rank; ++r) pr = fmaf(lam[r * 9 + t], __ldg(p.d + r * Cin + i), pr);
@@ -305,7 +309,7 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         __syncthreads();
       }
     }
-    for (int i = threadIdx.x; i < nW; i += kThreads) Wg[i] = Ws[i];
+    for (int i = threadIdx.x; i < nW; i += kLoopThreads) Wg[i] = Ws[i];
     __syncthreads();
   }
 }
@@ -364,9 +368,8 @@ int insert_loop_launch(const InsertLoopParams& p, cudaStream_t stream) {
     if (rc) return rc;
     attr = smem;
   }
-  int grid = device_sm_count();
-  if (grid > p.Cout) grid = p.Cout;
-  insert_loop_kernel<<<grid, kThreads, smem, stream>>>(p, p.key);
+  const int grid = p.Cout;     // one output channel per CTA
+  insert_loop_kernel<<<grid, kLoopThreads, smem, stream>>>(p, p.key);
   return check_cuda(cudaGetLastError(), "insert_loop launch");
 }
 

@@ -373,7 +373,7 @@ __global__ void add_noise_kernel(const float* __restrict__ x, const float* __res
 constexpr int BF_TY = 8, BF_TX = 16, BF_C = 64;
 constexpr int BF_PW = BF_TX + 3, BF_PH = BF_TY + 3;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
                      const float* __restrict__ k4, const float* __restrict__ noise,
                      long long noise_bstride, const float* __restrict__ noise_w,

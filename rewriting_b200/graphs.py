@@ -19,6 +19,10 @@ class GraphedModule(object):
         self.graph = None
         self.static_out = None
         self._warmup = warmup
+        self._copy_stream = torch.cuda.Stream()
+        self._stage = None          # two device staging buffers for pipelined D2H
+        self._stage_free = [None, None]
+        self._turn = 0
         self.refresh()
 
     def refresh(self):
@@ -35,10 +39,35 @@ class GraphedModule(object):
 
     def __call__(self, x, out=None):
         """Replays the forward on `x` (any device; copied into the static input).  Returns the
-        static output tensor (overwritten by the next call) or copies it into `out`."""
+        static output tensor (overwritten by the next call).  With a pinned host tensor `out`,
+        the result is moved to the host on a side stream through two staging buffers, so the
+        device->host copy of step i overlaps the compute of step i+1; call `sync()` before
+        reading `out`."""
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
-        if out is not None:
+        if out is None:
+            return self.static_out
+        if out.is_cuda:
             out.copy_(self.static_out, non_blocking=True)
             return out
-        return self.static_out
+        if self._stage is None:
+            self._stage = [torch.empty_like(self.static_out) for _ in range(2)]
+        i = self._turn
+        self._turn ^= 1
+        main = torch.cuda.current_stream()
+        if self._stage_free[i] is not None:           # the copy that last used this buffer
+            main.wait_event(self._stage_free[i])
+        self._stage[i].copy_(self.static_out, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            out.copy_(self._stage[i], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        self._stage_free[i] = done
+        return out
+
+    def sync(self):
+        """Wait for outstanding device->host copies issued by __call__(x, out=host)."""
+        self._copy_stream.synchronize()
