@@ -26,10 +26,7 @@ constexpr int kMaxW = 16;      // crop width handled by the register tile
 constexpr int kMaxRank = 32;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-// the insert loop runs one output channel per CTA, 4 warps, 4 CTAs per SM: all 512 channels
-// of a layer are resident at once (592 CTA slots) and their latency-bound phases interleave
-constexpr int kLoopThreads = 128;
-constexpr int kLoopWarps = kLoopThreads / 32;
+
 
 // out[o,i,t] = base[o,i,t] + sign * sum_r d[r,i] * (sum_j W[o,j,t] d[r,j])
 // one CTA per output channel o; row o of W is contiguous (Cin*taps floats).
@@ -66,53 +63,59 @@ project_rank_kernel(const float* __restrict__ w, const float* __restrict__ base,
 
 // ---------------------------------------------------------------------------
 // fused insert loop
+//
+// One CTA owns OC = 4 output channels and runs all iterations for them.  The key crop
+// (kpT, ~225 KB for 512 channels x 10 x 11) does not fit next to the weights in shared memory,
+// so it is streamed from L2 — the dominant cost.  Blocking four output channels per CTA makes
+// every loaded key value feed four accumulators (4x less L2 traffic than one channel per CTA:
+// measured 180 us -> see profiles), and the register tile is templated on the crop width.
 // ---------------------------------------------------------------------------
-struct LoopSmem {
-  // dynamic: W[Cin*9] | t[P] | gd[P] | red[...] ...
-};
+constexpr int OC = 4;
 
-__global__ void __launch_bounds__(kLoopThreads, 4)
+template <int MW>   // register tile width >= crop width w
+__global__ void __launch_bounds__(kThreads, 1)
 insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
   extern __shared__ float sm[];
   const int Cin = p.Cin, h = p.h, w = p.w, B = p.B;
   const int P = B * h * w;
   const int wp = w + 2;
   const int nW = Cin * 9;
-  float* Ws = sm;                 // [Cin*9]   current weight row
-  float* tS = Ws + nW;            // [P]       raw conv output t
-  float* gdS = tS + P;            // [P]       g * demod (wgrad coefficient)
-  float* dWS = gdS + P;           // [Cin*9]   only used for projections (aliased scratch)
-  float* lam = dWS + nW;          // [kMaxRank*9]
-  float* sc_b = lam + kMaxRank * 9;   // [B] demod, [B] coeff, loss, misc (64 floats)
-  float* demodS = sc_b;
-  float* coefS = sc_b + 16;
-  float* lossS = sc_b + 32;       // [kLoopWarps]
-  float* GS = sc_b + 40;          // [kLoopWarps*? ] per-warp partial G[b] -> B<=... stored [kLoopWarps][B<=2]?
+  float* Ws = sm;                      // [OC][Cin*9]   current weight rows
+  float* dWS = Ws + OC * nW;           // [OC][Cin*9]   gradient staging
+  float* tS = dWS + OC * nW;           // [OC][P]       raw conv output t
+  float* gdS = tS + OC * P;            // [OC][P]       g * demod (wgrad coefficient)
+  float* lam = gdS + OC * P;           // [OC][kMaxRank*9]
+  float* misc = lam + OC * kMaxRank * 9;
+  float* demodS = misc;                // [OC][4]
+  float* coefS = misc + 16;            // [OC][4]
+  float* lossS = misc + 32;            // [kWarps][OC]
+  float* GS = misc + 64;               // [kWarps][OC][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float sc = rsqrtf(static_cast<float>(Cin * 9));
-  const int nch = Cin / 32;       // channels per lane
+  const int nch = Cin / 32;            // channels per lane
   const float inv_numel = 1.0f / static_cast<float>(static_cast<long long>(B) * p.Cout * h * w);
 
-  for (int o = blockIdx.x; o < p.Cout; o += gridDim.x) {
-    float* Wg = p.W + static_cast<size_t>(o) * nW;
-    float* mg = p.m + static_cast<size_t>(o) * nW;
-    float* vg = p.v + static_cast<size_t>(o) * nW;
-    for (int i = threadIdx.x; i < nW; i += kLoopThreads) Ws[i] = Wg[i];
+  for (int o0 = blockIdx.x * OC; o0 < p.Cout; o0 += gridDim.x * OC) {
+    const int noc = (p.Cout - o0 < OC) ? p.Cout - o0 : OC;
+    for (int i = threadIdx.x; i < OC * nW; i += kThreads) {
+      const int oc = i / nW;
+      Ws[i] = (oc < noc) ? p.W[static_cast<size_t>(o0) * nW + i] : 0.f;
+    }
     __syncthreads();
 
     for (int step = 0; step < p.nsteps; ++step) {
       const int it = p.it0 + step;
-      // ---- demod[b] = rsqrt(sum_i style^2 * sum_uv (sc W)^2 + 1e-8), every warp redundantly
-      if (warp < B) {
-        const int b = warp;
+      // ---- demod[oc][b] = rsqrt(sum_i style^2 * sum_uv (sc W)^2 + 1e-8): warp <-> (oc, b)
+      for (int ob = warp; ob < OC * B; ob += kWarps) {
+        const int oc = ob / B, b = ob - oc * B;
         float acc = 0.f;
         for (int j = 0; j < nch; ++j) {
           const int i = lane + 32 * j;
           float ss = 0.f;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const float v = sc * Ws[i * 9 + t];
+            const float v = sc * Ws[oc * nW + i * 9 + t];
             ss = fmaf(v, v, ss);
           }
           const float s = __ldg(p.style + b * Cin + i);
@@ -120,94 +123,121 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) demodS[b] = rsqrtf(acc + 1e-8f);
+        if (lane == 0) demodS[oc * 4 + b] = rsqrtf(acc + 1e-8f);
       }
-      // ---- forward conv on the crop: warp <-> row units (b, y), lane <-> channel
-      for (int u = warp; u < B * h; u += kLoopWarps) {
+      // ---- forward conv on the crop: warp <-> row unit (b, y), lane <-> input channel;
+      //      every key value loaded feeds the OC output channels
+      for (int u = warp; u < B * h; u += kWarps) {
         const int b = u / h, y = u - b * h;
-        float acc[kMaxW];
+        float acc[OC][MW];
 #pragma unroll
-        for (int x = 0; x < kMaxW; ++x) acc[x] = 0.f;
+        for (int oc = 0; oc < OC; ++oc)
+#pragma unroll
+          for (int x = 0; x < MW; ++x) acc[oc][x] = 0.f;
         for (int j = 0; j < nch; ++j) {
           const int i = lane + 32 * j;
-          float wr[9];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) wr[t] = Ws[i * 9 + t];
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const float* krow = kpT + ((static_cast<size_t>(b) * (h + 2) + y + r) * wp) * Cin + i;
-            float kv[kMaxW + 2];
+            float kv[MW + 2];
 #pragma unroll
-            for (int x = 0; x < kMaxW + 2; ++x)
+            for (int x = 0; x < MW + 2; ++x)
               kv[x] = (x < wp) ? __ldg(krow + static_cast<size_t>(x) * Cin) : 0.f;
 #pragma unroll
-            for (int x = 0; x < kMaxW; ++x) {
-              acc[x] = fmaf(wr[r * 3 + 0], kv[x], acc[x]);
-              acc[x] = fmaf(wr[r * 3 + 1], kv[x + 1], acc[x]);
-              acc[x] = fmaf(wr[r * 3 + 2], kv[x + 2], acc[x]);
+            for (int oc = 0; oc < OC; ++oc) {
+              const float w0 = Ws[oc * nW + i * 9 + r * 3 + 0];
+              const float w1 = Ws[oc * nW + i * 9 + r * 3 + 1];
+              const float w2 = Ws[oc * nW + i * 9 + r * 3 + 2];
+#pragma unroll
+              for (int x = 0; x < MW; ++x) {
+                acc[oc][x] = fmaf(w0, kv[x], acc[oc][x]);
+                acc[oc][x] = fmaf(w1, kv[x + 1], acc[oc][x]);
+                acc[oc][x] = fmaf(w2, kv[x + 2], acc[oc][x]);
+              }
             }
           }
         }
 #pragma unroll
-        for (int x = 0; x < kMaxW; ++x) {
-          float a = acc[x];
+        for (int oc = 0; oc < OC; ++oc)
 #pragma unroll
-          for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          if (lane == x && x < w) tS[u * w + x] = sc * a;
+          for (int x = 0; x < MW; ++x) {
+            float a = acc[oc][x];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+            if (lane == x && x < w) tS[oc * P + u * w + x] = sc * a;
+          }
+      }
+      __syncthreads();
+      // ---- loss / output gradient: thread <-> (oc, pixel); block-reduce loss and G[oc][b]
+      {
+        float lsum[OC], gsum[OC][4];
+#pragma unroll
+        for (int oc = 0; oc < OC; ++oc) {
+          lsum[oc] = 0.f;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) gsum[oc][bb] = 0.f;
+        }
+        for (int q = threadIdx.x; q < P; q += kThreads) {
+          const int b = q / (h * w);
+          const int pp = q - b * h * w;
+          float nz = 0.f;
+          if (p.has_noise_act && p.noise) nz = p.noise_w * __ldg(p.noise + b * h * w + pp);
+#pragma unroll
+          for (int oc = 0; oc < OC; ++oc) {
+            if (oc >= noc) break;
+            const int o = o0 + oc;
+            const float t = tS[oc * P + q];
+            const float dm = demodS[oc * 4 + b];
+            float yv = t * dm;
+            float gate = 1.f;
+            if (p.has_noise_act) {
+              yv += nz;
+              yv += __ldg(p.bias + o);
+              gate = (yv > 0.f) ? 1.4142135623730951f : 0.2f * 1.4142135623730951f;
+              yv = (yv > 0.f ? yv : 0.2f * yv) * 1.4142135623730951f;
+            }
+            const float tgt = __ldg(p.target + (static_cast<size_t>(b) * p.Cout + o) * h * w + pp);
+            const float diff = yv - tgt;
+            lsum[oc] += fabsf(diff);
+            const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+            const float g = sgn * inv_numel * gate;
+            gdS[oc * P + q] = g * dm;
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (bb == b) gsum[oc][bb] += g * t;
+          }
+        }
+#pragma unroll
+        for (int oc = 0; oc < OC; ++oc) {
+#pragma unroll
+          for (int off = 16; off; off >>= 1) {
+            lsum[oc] += __shfl_xor_sync(0xffffffffu, lsum[oc], off);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              gsum[oc][bb] += __shfl_xor_sync(0xffffffffu, gsum[oc][bb], off);
+          }
+          if (lane == 0) {
+            lossS[warp * OC + oc] = lsum[oc];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) GS[(warp * OC + oc) * 4 + bb] = gsum[oc][bb];
+          }
         }
       }
       __syncthreads();
-      // ---- loss / output gradient, one thread per pixel; block-reduce loss and G[b]
-      float lsum = 0.f;
-      float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int q = threadIdx.x; q < P; q += kLoopThreads) {
-        const int b = q / (h * w);
-        const int pp = q - b * h * w;
-        const float t = tS[q];
-        float yv = t * demodS[b];
-        float gate = 1.f;
-        if (p.has_noise_act) {
-          if (p.noise) yv += p.noise_w * __ldg(p.noise + b * h * w + pp);
-          yv += __ldg(p.bias + o);
-          gate = (yv > 0.f) ? 1.4142135623730951f : 0.2f * 1.4142135623730951f;
-          yv = (yv > 0.f ? yv : 0.2f * yv) * 1.4142135623730951f;
-        }
-        const float tgt = __ldg(p.target + (static_cast<size_t>(b) * p.Cout + o) * h * w + pp);
-        const float diff = yv - tgt;
-        lsum += fabsf(diff);
-        const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
-        const float g = sgn * inv_numel * gate;
-        gdS[q] = g * demodS[b];
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb)
-          if (bb == b) gsum[bb] += g * t;
-      }
-#pragma unroll
-      for (int off = 16; off; off >>= 1) {
-        lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) gsum[bb] += __shfl_xor_sync(0xffffffffu, gsum[bb], off);
-      }
-      if (lane == 0) {
-        lossS[warp] = lsum;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) GS[warp * 4 + bb] = gsum[bb];
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < noc) {
         float l = 0.f;
-        for (int wv = 0; wv < kLoopWarps; ++wv) l += lossS[wv];
-        p.loss_out[static_cast<size_t>(step) * p.Cout + o] = l;
+        for (int wv = 0; wv < kWarps; ++wv) l += lossS[wv * OC + threadIdx.x];
+        p.loss_out[static_cast<size_t>(step) * p.Cout + o0 + threadIdx.x] = l;
       }
-      if (threadIdx.x < B) {
+      if (threadIdx.x < OC * 4) {
+        const int oc = threadIdx.x >> 2, bb = threadIdx.x & 3;
         float G = 0.f;
-        for (int wv = 0; wv < kLoopWarps; ++wv) G += GS[wv * 4 + threadIdx.x];
-        const float dm = demodS[threadIdx.x];
-        coefS[threadIdx.x] = G * dm * dm * dm;
+        for (int wv = 0; wv < kWarps; ++wv) G += GS[(wv * OC + oc) * 4 + bb];
+        const float dm = demodS[oc * 4 + bb];
+        coefS[oc * 4 + bb] = (bb < B) ? G * dm * dm * dm : 0.f;
       }
       __syncthreads();
 
-      // ---- weight gradient: warp <-> channel pair, lane <-> channel; 9 accumulators each
       // Adam bias corrections as torch.optim.Adam computes them (python doubles)
       const double stepd = static_cast<double>(it + 1);
       const double bc1 = 1.0 - pow(static_cast<double>(p.beta1), stepd);
@@ -217,101 +247,137 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       const float one_m_b1 = 1.0f - p.beta1;
       const float one_m_b2 = 1.0f - p.beta2;
 
-      for (int j = warp; j < nch; j += kLoopWarps) {
+      // ---- weight gradient: warp <-> channel group j, lane <-> input channel; OC x 9 accumulators
+      for (int j = warp; j < nch; j += kWarps) {
         const int i = lane + 32 * j;
-        float acc[9];
+        float acc[OC][9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+        for (int oc = 0; oc < OC; ++oc)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[oc][t] = 0.f;
         for (int b = 0; b < B; ++b) {
           for (int y = 0; y < h; ++y) {
-            float gv[kMaxW];
-#pragma unroll
-            for (int x = 0; x < kMaxW; ++x) gv[x] = (x < w) ? gdS[(b * h + y) * w + x] : 0.f;
+            float kv[3][MW + 2];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               const float* krow = kpT + ((static_cast<size_t>(b) * (h + 2) + y + r) * wp) * Cin + i;
-              float kv[kMaxW + 2];
 #pragma unroll
-              for (int x = 0; x < kMaxW + 2; ++x)
-                kv[x] = (x < wp) ? __ldg(krow + static_cast<size_t>(x) * Cin) : 0.f;
+              for (int x = 0; x < MW + 2; ++x)
+                kv[r][x] = (x < wp) ? __ldg(krow + static_cast<size_t>(x) * Cin) : 0.f;
+            }
 #pragma unroll
-              for (int x = 0; x < kMaxW; ++x) {
-                acc[r * 3 + 0] = fmaf(gv[x], kv[x], acc[r * 3 + 0]);
-                acc[r * 3 + 1] = fmaf(gv[x], kv[x + 1], acc[r * 3 + 1]);
-                acc[r * 3 + 2] = fmaf(gv[x], kv[x + 2], acc[r * 3 + 2]);
+            for (int oc = 0; oc < OC; ++oc) {
+#pragma unroll
+              for (int x = 0; x < MW; ++x) {
+                const float gv = (x < w) ? gdS[oc * P + (b * h + y) * w + x] : 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                  acc[oc][r * 3 + 0] = fmaf(gv, kv[r][x], acc[oc][r * 3 + 0]);
+                  acc[oc][r * 3 + 1] = fmaf(gv, kv[r][x + 1], acc[oc][r * 3 + 1]);
+                  acc[oc][r * 3 + 2] = fmaf(gv, kv[r][x + 2], acc[oc][r * 3 + 2]);
+                }
               }
             }
           }
         }
         // demod term: - sc^2 * W * sum_b coef[b] * style[b,i]^2
-        float cs = 0.f;
-        for (int b = 0; b < B; ++b) {
-          const float s = __ldg(p.style + b * Cin + i);
-          cs = fmaf(coefS[b], s * s, cs);
-        }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float wv = Ws[i * 9 + t];
-          const float g = sc * acc[t] - (sc * sc) * wv * cs;
-          dWS[i * 9 + t] = g;
+        for (int oc = 0; oc < OC; ++oc) {
+          float cs = 0.f;
+          for (int b = 0; b < B; ++b) {
+            const float s = __ldg(p.style + b * Cin + i);
+            cs = fmaf(coefS[oc * 4 + b], s * s, cs);
+          }
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float wv = Ws[oc * nW + i * 9 + t];
+            dWS[oc * nW + i * 9 + t] = sc * acc[oc][t] - (sc * sc) * wv * cs;
+          }
         }
       }
       __syncthreads();
       // ---- optional gradient projection onto span(d)   (ganrewrite.py:285-286)
       if (p.project_gradient) {
-        for (int rt = warp; rt < p.rank * 9; rt += kLoopWarps) {
+        for (int ort = warp; ort < OC * p.rank * 9; ort += kWarps) {
+          const int oc = ort / (p.rank * 9), rt = ort - oc * p.rank * 9;
           const int r = rt / 9, t = rt - r * 9;
           float a = 0.f;
-          for (int i = lane; i < Cin; i += 32) a = fmaf(dWS[i * 9 + t], __ldg(p.d + r * Cin + i), a);
+          for (int i = lane; i < Cin; i += 32)
+            a = fmaf(dWS[oc * nW + i * 9 + t], __ldg(p.d + r * Cin + i), a);
 #pragma unroll
           for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          if (lane == 0) lam[rt] = a;
+          if (lane == 0) lam[oc * kMaxRank * 9 + rt] = a;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
-          const int i = e / 9, t = e - i * 9;
+        for (int e = threadIdx.x; e < OC * nW; e += kThreads) {
+          const int oc = e / nW, ei = e - oc * nW;
+          const int i = ei / 9, t = ei - i * 9;
           float pr = 0.f;
-          for (int r = 0; r < p.rank; ++r) pr = fmaf(lam[r * 9 + t], __ldg(p.d + r * Cin + i), pr);
+          for (int r = 0; r < p.rank; ++r)
+            pr = fmaf(lam[oc * kMaxRank * 9 + r * 9 + t], __ldg(p.d + r * Cin + i), pr);
           dWS[e] = pr;
         }
         __syncthreads();
       }
       // ---- Adam (torch.optim.Adam, amsgrad=False, weight_decay=0)
-      for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
+      for (int e = threadIdx.x; e < noc * nW; e += kThreads) {
+        const size_t ge = static_cast<size_t>(o0) * nW + e;
         const float g = dWS[e];
-        float mm = mg[e], vv = vg[e];
+        float mm = p.m[ge], vv = p.v[ge];
         mm = mm + (g - mm) * one_m_b1;                 // exp_avg.lerp_(grad, 1-beta1)
         vv = vv * p.beta2 + one_m_b2 * g * g;          // mul_(beta2).addcmul_(g, g, 1-beta2)
-        mg[e] = mm;
-        vg[e] = vv;
+        p.m[ge] = mm;
+        p.v[ge] = vv;
         const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
         Ws[e] = Ws[e] - step_size * (mm / denom);
       }
       __syncthreads();
       // ---- periodic projection  W <- W_ortho + P_d(W)   (ganrewrite.py:291-294)
       if (p.w_ortho != nullptr && (it % p.piter == 0 || it == p.niter_total - 1)) {
-        for (int rt = warp; rt < p.rank * 9; rt += kLoopWarps) {
+        for (int ort = warp; ort < OC * p.rank * 9; ort += kWarps) {
+          const int oc = ort / (p.rank * 9), rt = ort - oc * p.rank * 9;
           const int r = rt / 9, t = rt - r * 9;
           float a = 0.f;
-          for (int i = lane; i < Cin; i += 32) a = fmaf(Ws[i * 9 + t], __ldg(p.d + r * Cin + i), a);
+          for (int i = lane; i < Cin; i += 32)
+            a = fmaf(Ws[oc * nW + i * 9 + t], __ldg(p.d + r * Cin + i), a);
 #pragma unroll
           for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          if (lane == 0) lam[rt] = a;
+          if (lane == 0) lam[oc * kMaxRank * 9 + rt] = a;
         }
         __syncthreads();
-        const float* wo = p.w_ortho + static_cast<size_t>(o) * nW;
-        for (int e = threadIdx.x; e < nW; e += kLoopThreads) {
-          const int i = e / 9, t = e - i * 9;
+        for (int e = threadIdx.x; e < noc * nW; e += kThreads) {
+          const int oc = e / nW, ei = e - oc * nW;
+          const int i = ei / 9, t = ei - i * 9;
           float pr = 0.f;
-          for (int r = 0; r < p.rank; ++r) pr = fmaf(lam[r * 9 + t], __ldg(p.d + r * Cin + i), pr);
-          Ws[e] = __ldg(wo + e) + pr;
+          for (int r = 0; r < p.rank; ++r)
+            pr = fmaf(lam[oc * kMaxRank * 9 + r * 9 + t], __ldg(p.d + r * Cin + i), pr);
+          Ws[e] = __ldg(p.w_ortho + static_cast<size_t>(o0) * nW + e) + pr;
         }
         __syncthreads();
       }
     }
-    for (int i = threadIdx.x; i < nW; i += kLoopThreads) Wg[i] = Ws[i];
+    for (int i = threadIdx.x; i < noc * nW; i += kThreads)
+      p.W[static_cast<size_t>(o0) * nW + i] = Ws[i];
     __syncthreads();
   }
+}
+
+template <int MW>
+static int launch_insert(const InsertLoopParams& p, size_t smem, cudaStream_t stream) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    int rc = check_cuda(cudaFuncSetAttribute(insert_loop_kernel<MW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)),
+                        "insert_loop smem attr");
+    if (rc) return rc;
+    attr = smem;
+  }
+  int grid = (p.Cout + OC - 1) / OC;
+  const int sms = device_sm_count();
+  if (grid > sms) grid = sms;
+  insert_loop_kernel<MW><<<grid, kThreads, smem, stream>>>(p, p.key);
+  return check_cuda(cudaGetLastError(), "insert_loop launch");
 }
 
 }  // namespace
@@ -346,7 +412,7 @@ int project_rank_launch_signed(const float* w, const float* base, const float* d
 }
 
 int insert_loop_launch(const InsertLoopParams& p, cudaStream_t stream) {
-  if (p.w > kMaxW || p.B > 4 || p.B < 1 || p.Cin % 32 != 0 || p.rank > kMaxRank ||
+  if (p.w > kMaxW || p.B > 4 || p.B < 1 || p.Cin % 32 != 0 || p.rank > kMaxRank || p.rank < 1 ||
       static_cast<long long>(p.B) * p.h * p.w > 4096) {
     set_last_error("insert_loop: unsupported crop B=%d h=%d w=%d Cin=%d rank=%d", p.B, p.h, p.w,
                    p.Cin, p.rank);
@@ -354,23 +420,15 @@ int insert_loop_launch(const InsertLoopParams& p, cudaStream_t stream) {
   }
   const int P = p.B * p.h * p.w;
   const int nW = p.Cin * 9;
-  const size_t smem = (static_cast<size_t>(2 * nW) + 2 * P + kMaxRank * 9 + 128) * sizeof(float);
-  if (smem > 220 * 1024) {
+  const size_t smem = (static_cast<size_t>(2 * OC) * nW + static_cast<size_t>(2 * OC) * P +
+                       OC * kMaxRank * 9 + 64 + kWarps * OC * 5 + 64) * sizeof(float);
+  if (smem > 225 * 1024) {
     set_last_error("insert_loop: shared memory %zu B too large", smem);
     return RW_ERR_UNSUPPORTED;
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    int rc = check_cuda(cudaFuncSetAttribute(insert_loop_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)),
-                        "insert_loop smem attr");
-    if (rc) return rc;
-    attr = smem;
-  }
-  const int grid = p.Cout;     // one output channel per CTA
-  insert_loop_kernel<<<grid, kLoopThreads, smem, stream>>>(p, p.key);
-  return check_cuda(cudaGetLastError(), "insert_loop launch");
+  if (p.w <= 8) return launch_insert<8>(p, smem, stream);
+  if (p.w <= 12) return launch_insert<12>(p, smem, stream);
+  return launch_insert<16>(p, smem, stream);
 }
 
 }  // namespace rw
