@@ -22,6 +22,9 @@
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM
 // alloc), warps 2..5 = epilogue (TMEM -> regs -> global).  Persistent CTAs,
 // 3-stage smem ring, double-buffered TMEM accumulators.
+#include <cstdlib>
+#include <cstring>
+
 #include "rw_common.cuh"
 #include "rw_kernels.h"
 
@@ -43,36 +46,42 @@ constexpr int kNumThreads = 192;
 constexpr int kChunkKB = 8;
 constexpr int kNumAcc = 4;
 
-template <int BN>
+// CG = cta_group: 1 = one CTA per 128-row tile; 2 = CTA pair, 256-row tile, each CTA stages its
+// own 128 A rows and HALF of the B (weight) tile -> 25 % less shared-memory traffic per MMA,
+// which is what bounds the 1-CTA kernel (A 4 KB + B 4 KB read per 64-cycle MMA = 125 B/cycle).
+template <int BN, int CG>
 struct ConvSmem {
-  static constexpr int kABytes = BM * BK * 2;   // one plane
-  static constexpr int kBBytes = BN * BK * 2;   // one plane
+  static constexpr int kStagesN = (CG == 2) ? 4 : kStages;
+  static constexpr int kABytes = BM * BK * 2;          // one plane
+  static constexpr int kBBytes = (BN / CG) * BK * 2;   // one plane (this CTA's share)
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   // per-epilogue-warp transpose scratch: 32 rows x (128 B + 16 B pad)
   static constexpr int kScratchRow = 144;
   static constexpr int kScratchBytes = 4 * 32 * kScratchRow;
-  static constexpr int kTotal = kStages * kStageBytes + kScratchBytes + 1024 /*align slack*/ +
+  static constexpr int kTotal = kStagesN * kStageBytes + kScratchBytes + 1024 /*align slack*/ +
                                 256 /*barriers*/;
 };
 
 struct Barriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[4];
+  uint64_t empty[4];
   uint64_t tmem_full[kNumAcc];
   uint64_t tmem_empty[kNumAcc];
   uint32_t tmem_base;
 };
 
 // tile -> (phase, mn).  Phases have very different tap counts (4/2/2/1 for a stride-2
-// conv_transpose); with a static round-robin over a grid that is a multiple of nphase every CTA
-// would always draw the same phase, so the phase is rotated by the CTA's iteration index.
-__device__ __forceinline__ void decode_tile(int tile, int nphase, int& ph, int& mn) {
+// conv_transpose); with a static round-robin every scheduler slot would keep drawing the same
+// one or two phases, so the phase is rotated by the (m, n) group index — a bijection inside
+// every group of `nphase` consecutive tiles.
+__device__ __forceinline__ void decode_tile(int tile, int nphase, int nsched, int& ph, int& mn) {
+  (void)nsched;
   mn = tile / nphase;
   ph = tile - mn * nphase;
-  if (nphase > 1 && (gridDim.x % nphase) == 0) ph = (ph + tile / static_cast<int>(gridDim.x)) % nphase;
+  if (nphase > 1) ph = (ph + mn) % nphase;
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
@@ -81,14 +90,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  using S = ConvSmem<BN>;
-  uint8_t* scratch_base = smem + kStages * S::kStageBytes;
+  using S = ConvSmem<BN, CG>;
+  constexpr int kSt = S::kStagesN;
+  uint8_t* scratch_base = smem + kSt * S::kStageBytes;
   Barriers* bars = reinterpret_cast<Barriers*>(scratch_base + S::kScratchBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = (cta_rank == 0);
+  const int sched_id = blockIdx.x / CG;          // tile scheduler slot (one per CTA / CTA pair)
+  const int nsched = gridDim.x / CG;
 
-  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int m_tiles = (p.rows + BM * CG - 1) / (BM * CG);
   const int n_tiles = p.Cout / BN;
   const int mn_tiles = m_tiles * n_tiles;
   const int num_tiles = mn_tiles * p.nphase;
@@ -99,21 +113,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_w_hi);
     tma_prefetch_desc(&map_w_lo);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kSt; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < kNumAcc; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4);
+      mbar_init(&bars->tmem_empty[s], 4 * CG);   // epilogue warps of every CTA of the pair
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<kNumAcc * BN>(&bars->tmem_base);
+    if constexpr (CG == 2) tmem_alloc_cg2<kNumAcc * BN>(&bars->tmem_base);
+    else tmem_alloc<kNumAcc * BN>(&bars->tmem_base);
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // peer barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -122,11 +138,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += nsched) {
         int ph, mn;
-        decode_tile(tile, p.nphase, ph, mn);
-        const int n0 = (mn % n_tiles) * BN;
-        const int m0 = (mn / n_tiles) * BM;
+        decode_tile(tile, p.nphase, nsched, ph, mn);
+        const int n0 = (mn % n_tiles) * BN + cta_rank * (BN / CG);
+        const int m0 = (mn / n_tiles) * BM * CG + cta_rank * BM;
         for (int t = 0; t < p.ph_ntaps[ph]; ++t) {
           const int arow = m0 + p.ph_shift[ph][t];
           const int wcol = p.ph_kofs[ph][t];
@@ -134,28 +150,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           for (int kb = 0; kb < kb_per_tap; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             uint8_t* st = smem + stage * S::kStageBytes;
-            mbar_expect_tx(&bars->full[stage], S::kStageBytes);
-            tma_load_2d(st, &map_a_hi, &bars->full[stage], acol + kb * BK, arow);
-            tma_load_2d(st + S::kABytes, &map_a_lo, &bars->full[stage], acol + kb * BK, arow);
-            tma_load_2d(st + 2 * S::kABytes, &map_w_hi, &bars->full[stage], wcol + kb * BK, n0);
-            tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_w_lo, &bars->full[stage],
-                        wcol + kb * BK, n0);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if constexpr (CG == 2) {
+              // both CTAs' bytes are credited to the leader's full barrier
+              if (leader) mbar_expect_tx(&bars->full[stage], 2 * S::kStageBytes);
+              tma_load_2d_cg2(st, &map_a_hi, &bars->full[stage], acol + kb * BK, arow);
+              tma_load_2d_cg2(st + S::kABytes, &map_a_lo, &bars->full[stage], acol + kb * BK, arow);
+              tma_load_2d_cg2(st + 2 * S::kABytes, &map_w_hi, &bars->full[stage], wcol + kb * BK, n0);
+              tma_load_2d_cg2(st + 2 * S::kABytes + S::kBBytes, &map_w_lo, &bars->full[stage],
+                              wcol + kb * BK, n0);
+            } else {
+              mbar_expect_tx(&bars->full[stage], S::kStageBytes);
+              tma_load_2d(st, &map_a_hi, &bars->full[stage], acol + kb * BK, arow);
+              tma_load_2d(st + S::kABytes, &map_a_lo, &bars->full[stage], acol + kb * BK, arow);
+              tma_load_2d(st + 2 * S::kABytes, &map_w_hi, &bars->full[stage], wcol + kb * BK, n0);
+              tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_w_lo, &bars->full[stage],
+                          wcol + kb * BK, n0);
+            }
+            if (++stage == kSt) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = sched_id; tile < num_tiles; tile += nsched) {
       int ph_m, mn_m;
-      decode_tile(tile, p.nphase, ph_m, mn_m);
+      decode_tile(tile, p.nphase, nsched, ph_m, mn_m);
       const int num_kb = p.ph_ntaps[ph_m] * kb_per_tap;
-      if (lane == 0) {
+      if (lane == 0 && leader) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
           const int as = chunk % kNumAcc;
           const uint32_t aphase = (chunk / kNumAcc) & 1u;
@@ -176,14 +202,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             for (int kk = 0; kk < BK / UMMA_K; ++kk) {
               const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
               // smallest terms first, then the dominant hi*hi product
-              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
-              umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+              if constexpr (CG == 2) {
+                umma_bf16_cg2(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                umma_bf16_cg2(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                umma_bf16_cg2(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+              } else {
+                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+              }
             }
-            umma_commit(&bars->empty[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if constexpr (CG == 2) umma_commit_cg2_mc(&bars->empty[stage]);
+            else umma_commit(&bars->empty[stage]);
+            if (++stage == kSt) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&bars->tmem_full[as]);
+          if constexpr (CG == 2) umma_commit_cg2_mc(&bars->tmem_full[as]);
+          else umma_commit(&bars->tmem_full[as]);
         }
       }
       __syncwarp();
@@ -193,13 +227,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int img = p.Hp * p.Wp;
     uint32_t chunk = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = sched_id; tile < num_tiles; tile += nsched) {
       int ph, mn;
-      decode_tile(tile, p.nphase, ph, mn);
+      decode_tile(tile, p.nphase, nsched, ph, mn);
       const int num_kb = p.ph_ntaps[ph] * kb_per_tap;
       const int Hv = p.ph_Hv[ph], Wv = p.ph_Wv[ph];
       const int n0 = (mn % n_tiles) * BN;
-      const int m0 = (mn / n_tiles) * BM;
+      const int m0 = (mn / n_tiles) * BM * CG + cta_rank * BM;
       const int prow = m0 + q * 32 + lane;
       const int b = prow / img;
       const int rem = prow - b * img;
@@ -236,7 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&bars->tmem_empty[as]);
+          else mbar_arrive(&bars->tmem_empty[as]);
+        }
       }
 
       // ---- fused epilogue -------------------------------------------------------------
@@ -343,13 +380,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // the peer may still signal our barriers / TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kNumAcc * BN>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<kNumAcc * BN>(tmem_base);
+    else tmem_dealloc<kNumAcc * BN>(tmem_base);
   }
 }
 
 }  // namespace
+
+template <int CG>
+static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void* a_lo,
+                             const void* w_hi, const void* w_lo, int wk_total,
+                             cudaStream_t stream) {
+  constexpr int BN = 128;
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  int rc;
+  const int a_cols = p.a_cols > 0 ? p.a_cols : p.Cin;
+  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN / CG)))
+    return rc;
+  if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN / CG)))
+    return rc;
+
+  using S = ConvSmem<BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, CG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+                    "conv_tc smem attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int m_tiles = (p.rows + BM * CG - 1) / (BM * CG);
+  const int n_tiles = p.Cout / BN;
+  const int num_tiles = m_tiles * n_tiles * p.nphase;
+  int sched = device_sm_count() / CG;
+  if (sched > num_tiles) sched = num_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(sched * CG);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CG>, ma_hi, ma_lo, mw_hi, mw_lo, p),
+                    "conv_tc launch");
+}
+
+// 0 = automatic (CTA pairs when the launch has at least one full wave of 256-row tiles),
+// 1 / 2 = forced (tests, RW_CONV_CG environment variable)
+static int g_conv_cg = -1;
 
 int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
                    const void* w_lo, int wk_total, cudaStream_t stream) {
@@ -364,32 +453,17 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
       set_last_error("conv_tc: phase %d has %d taps", i, p.ph_ntaps[i]);
       return RW_ERR_BAD_ARG;
     }
-  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-  int rc;
-  const int a_cols = p.a_cols > 0 ? p.a_cols : p.Cin;
-  if ((rc = make_tmap_2d_bf16(&ma_hi, a_hi, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&ma_lo, a_lo, a_cols, p.rows, (uint64_t)a_cols * 2, BK, BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))
-    return rc;
-  if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, wk_total, p.Cout, (uint64_t)wk_total * 2, BK, BN)))
-    return rc;
-
-  using S = ConvSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
-                    "conv_tc smem attr");
-    if (rc) return rc;
-    attr_set = true;
+  if (g_conv_cg < 0) {
+    const char* e = getenv("RW_CONV_CG");
+    g_conv_cg = e ? atoi(e) : 0;
   }
-  const int m_tiles = (p.rows + BM - 1) / BM;
-  const int n_tiles = p.Cout / BN;
-  const int num_tiles = m_tiles * n_tiles * p.nphase;
-  int grid = device_sm_count();
-  if (grid > num_tiles) grid = num_tiles;
-  conv_tc_kernel<BN><<<grid, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
-  return check_cuda(cudaGetLastError(), "conv_tc launch");
+  int cg = g_conv_cg;
+  if (cg != 1 && cg != 2) {
+    const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
+    cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
+  }
+  if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
 }
 
 }  // namespace rw
