@@ -44,7 +44,16 @@ constexpr int kNumThreads = 192;
 // fp32 registers with round-to-nearest.  kNumAcc TMEM buffers form a ring between the MMA
 // issuer and the epilogue.
 constexpr int kChunkKB = 8;
-constexpr int kNumAcc = 4;
+// Measured (tools/cuda/mma_rate.cu, profiles/r1_mma_rate.txt): an M=128,K=16 bf16 MMA costs
+// 75 cycles for N <= 128 but 128 cycles for N = 256, i.e. N=128 instructions run the tensor
+// pipe at 85 % at best.  The single-CTA kernel therefore issues the two products that share
+// A_hi as ONE N=256 instruction against the concatenated [B_hi ; B_lo] tile (adjacent in the
+// stage): D[:,0:128] += A_hi B_hi^T, D[:,128:256] += A_hi B_lo^T, then A_lo B_hi^T into
+// D[:,0:128] (203 instead of 225 cycles per k-step).  The epilogue adds the two halves.
+template <int CG> struct AccGeom {
+  static constexpr int kAccCols = (CG == 1) ? 256 : 128;   // TMEM columns per accumulator
+  static constexpr int kNumAcc = 512 / kAccCols;           // ring depth
+};
 
 // CG = cta_group: 1 = one CTA per 128-row tile; 2 = CTA pair, 256-row tile, each CTA stages its
 // own 128 A rows and HALF of the B (weight) tile -> 25 % less shared-memory traffic per MMA,
@@ -65,8 +74,8 @@ struct ConvSmem {
 struct Barriers {
   uint64_t full[4];
   uint64_t empty[4];
-  uint64_t tmem_full[kNumAcc];
-  uint64_t tmem_empty[kNumAcc];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
   uint32_t tmem_base;
 };
 
@@ -75,10 +84,9 @@ struct Barriers {
 // one or two phases, so the phase is rotated by the (m, n) group index — a bijection inside
 // every group of `nphase` consecutive tiles.
 __device__ __forceinline__ void decode_tile(int tile, int nphase, int nsched, int& ph, int& mn) {
-  (void)nsched;
   mn = tile / nphase;
   ph = tile - mn * nphase;
-  if (nphase > 1) ph = (ph + mn) % nphase;
+  if (nphase > 1) ph = (ph + ((nsched % nphase) == 0 ? tile / nsched : mn)) % nphase;
 }
 
 template <int BN, int CG>
@@ -92,6 +100,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                              ~static_cast<uintptr_t>(1023));
   using S = ConvSmem<BN, CG>;
   constexpr int kSt = S::kStagesN;
+  constexpr int kNumAcc = AccGeom<CG>::kNumAcc;
+  constexpr int kAccCols = AccGeom<CG>::kAccCols;
+  static_assert(BN == 128, "accumulator geometry assumes 128-column tiles");
   uint8_t* scratch_base = smem + kSt * S::kStageBytes;
   Barriers* bars = reinterpret_cast<Barriers*>(scratch_base + S::kScratchBytes);
 
@@ -124,8 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     fence_mbar_init();
   }
   if (warp == 1) {
-    if constexpr (CG == 2) tmem_alloc_cg2<kNumAcc * BN>(&bars->tmem_base);
-    else tmem_alloc<kNumAcc * BN>(&bars->tmem_base);
+    if constexpr (CG == 2) tmem_alloc_cg2<512>(&bars->tmem_base);
+    else tmem_alloc<512>(&bars->tmem_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -174,6 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, 0, 0);
+    constexpr uint32_t idesc_n256 = make_idesc_bf16(BM, 2 * BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
@@ -187,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t aphase = (chunk / kNumAcc) & 1u;
           mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + as * BN;
+          const uint32_t tmem_d = tmem_base + as * kAccCols;
           const int kb_end = (kb0 + kChunkKB < num_kb) ? kb0 + kChunkKB : num_kb;
           for (int kb = kb0; kb < kb_end; ++kb) {
             mbar_wait(&bars->full[stage], phase);
@@ -207,9 +219,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 umma_bf16_cg2(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
                 umma_bf16_cg2(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
               } else {
-                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
-                umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+                // [B_hi ; B_lo] are adjacent 128-row tiles: one N=256 operand
+                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc_n256, ((kb - kb0) | kk) != 0);
+                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1u);
               }
             }
             if constexpr (CG == 2) umma_commit_cg2_mc(&bars->empty[stage]);
@@ -261,12 +273,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN + c0) +
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kAccCols + c0) +
                                  (static_cast<uint32_t>(q * 32) << 16);
           tmem_ld_32x32(taddr, v);
-          tmem_ld_wait();
+          if constexpr (CG == 1) {
+            uint32_t v2[32];                       // the A_hi * B_lo half
+            tmem_ld_32x32(taddr + BN, v2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j)
+              acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -383,8 +404,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   if constexpr (CG == 2) cluster_sync_all();     // the peer may still signal our barriers / TMEM
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (CG == 2) tmem_dealloc_cg2<kNumAcc * BN>(tmem_base);
-    else tmem_dealloc<kNumAcc * BN>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -432,6 +453,10 @@ static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (CG == 1) {
+    conv_tc_kernel<BN, 1><<<sched, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    return check_cuda(cudaGetLastError(), "conv_tc launch");
+  }
   return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CG>, ma_hi, ma_lo, mw_hi, mw_lo, p),
                     "conv_tc launch");
 }
@@ -459,8 +484,9 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
   }
   int cg = g_conv_cg;
   if (cg != 1 && cg != 2) {
-    const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
-    cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
+    // measured: the CTA-pair variant does not beat the single-CTA kernel once the latter issues
+    // N=256 MMAs (the per-instruction floor, not shared-memory bandwidth, was the limiter)
+    cg = 1;
   }
   if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
   return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
