@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librw_b200.so')
+LIB_PATH = os.environ.get('RW_LIB') or os.path.join(_HERE, 'librw_b200.so')
 
 c_int = ctypes.c_int
 c_ll = ctypes.c_longlong

@@ -45,13 +45,12 @@ constexpr int kNumThreads = 192;
 // issuer and the epilogue.
 constexpr int kChunkKB = 8;
 // Measured (tools/cuda/mma_rate.cu, profiles/r1_mma_rate.txt): an M=128,K=16 bf16 MMA costs
-// 75 cycles for N <= 128 but 128 cycles for N = 256, i.e. N=128 instructions run the tensor
-// pipe at 85 % at best.  The single-CTA kernel therefore issues the two products that share
-// A_hi as ONE N=256 instruction against the concatenated [B_hi ; B_lo] tile (adjacent in the
-// stage): D[:,0:128] += A_hi B_hi^T, D[:,128:256] += A_hi B_lo^T, then A_lo B_hi^T into
-// D[:,0:128] (203 instead of 225 cycles per k-step).  The epilogue adds the two halves.
+// 75 cycles for N <= 128 and 128 cycles for N = 256.  Issuing A_hi x [B_hi ; B_lo] as one N=256
+// instruction (203 instead of 225 cycles per k-step) was tried and changed nothing: the kernel
+// is bound by the depth of the TMA pipeline (bytes in flight vs L2 latency), not by the tensor
+// pipe, so the simpler three N=128 products are kept.
 template <int CG> struct AccGeom {
-  static constexpr int kAccCols = (CG == 1) ? 256 : 128;   // TMEM columns per accumulator
+  static constexpr int kAccCols = 128;                     // TMEM columns per accumulator
   static constexpr int kNumAcc = 512 / kAccCols;           // ring depth
 };
 
@@ -185,7 +184,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, 0, 0);
-    constexpr uint32_t idesc_n256 = make_idesc_bf16(BM, 2 * BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
@@ -219,9 +217,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 umma_bf16_cg2(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
                 umma_bf16_cg2(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
               } else {
-                // [B_hi ; B_lo] are adjacent 128-row tiles: one N=256 operand
-                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc_n256, ((kb - kb0) | kk) != 0);
-                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1u);
+                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
               }
             }
             if constexpr (CG == 2) umma_commit_cg2_mc(&bars->empty[stage]);
@@ -276,18 +274,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kAccCols + c0) +
                                  (static_cast<uint32_t>(q * 32) << 16);
           tmem_ld_32x32(taddr, v);
-          if constexpr (CG == 1) {
-            uint32_t v2[32];                       // the A_hi * B_lo half
-            tmem_ld_32x32(taddr + BN, v2);
-            tmem_ld_wait();
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
         }
         tc_fence_before();
         __syncwarp();
@@ -484,9 +473,10 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
   }
   int cg = g_conv_cg;
   if (cg != 1 && cg != 2) {
-    // measured: the CTA-pair variant does not beat the single-CTA kernel once the latter issues
-    // N=256 MMAs (the per-instruction floor, not shared-memory bandwidth, was the limiter)
-    cg = 1;
+    // CTA pairs (4 stages of 48 KB, 25 % fewer bytes per MMA) for launches with at least one
+    // full wave of 256-row tiles; the single-CTA kernel for the small layers
+    const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
+    cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
   }
   if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
   return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
