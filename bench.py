@@ -357,10 +357,13 @@ def main():
     if not args.no_extra:
         from rewriting_b200 import fastpath
         with torch.no_grad():
+            # what SeqStyleGanRewriter.collect_2nd_moment does per batch: generator up to layer
+            # 8's conv (CUDA-graph replay), whose operand planes are the keys, then the col-GEMM
+            key_runner = GraphedModule(lambda zz: fastpath.forward(model, zz, upto_key_layer=8),
+                                       z_dev[:COV_BATCH])
+
             def cov_step(zb, r2m):
-                # what SeqStyleGanRewriter.collect_2nd_moment does per batch: generator up to
-                # layer 8's conv, whose operand planes are the keys, then the col-GEMM
-                planes = fastpath.forward(model, zb, upto_key_layer=8)
+                planes = key_runner(zb)
                 r2m.add_planes(planes.hi, planes.lo, planes.B * planes.H * planes.W)
             r2m = runningstats.RunningSecondMoment()
             for i in range(W):

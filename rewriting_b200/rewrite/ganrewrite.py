@@ -144,10 +144,27 @@ class ProgressiveGanRewriter(object):
         z = zbatch.to(self.device)
         m = _DCONV_RE.match(self.firstlayer)
         if m and isinstance(self.model, sg2.SeqStyleGAN2) and fastpath.eligible(self.model, z):
-            return fastpath.forward(self.model, z, upto_key_layer=int(m.group(1)))
+            return self._graphed_key_planes(z, int(m.group(1)))
         acts = self.context_acts(self.context_model(z))
         planes, _ = ops.prep_keys(acts, None)
         return planes
+
+    def _graphed_key_planes(self, z, layer):
+        """The context pass for one z batch is ~40 short kernels (launch-bound at the reference's
+        batch size of 10), so it is captured once per batch shape into a CUDA graph and replayed;
+        the capture is redone if any parameter changed since (edits bump `_version`)."""
+        from .. import fastpath
+        from ..graphs import GraphedModule
+        versions = tuple(p._version for p in self.model.parameters())
+        key = (tuple(z.shape), layer)
+        cache = self.__dict__.setdefault('_key_graphs', {})
+        ent = cache.get(key)
+        if ent is None or ent[0] != versions:
+            model = self.model
+            fn = lambda zz: fastpath.forward(model, zz, upto_key_layer=layer)
+            ent = (versions, GraphedModule(fn, z))
+            cache[key] = ent
+        return ent[1](z)
 
     def collect_2nd_moment(self):
         """C = E[k k^T] (uncentered), computed or loaded from `r2m.npz` [ganrewrite.py:83-96].
