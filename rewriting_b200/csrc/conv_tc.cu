@@ -117,6 +117,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int mn_tiles = m_tiles * n_tiles;
   const int num_tiles = mn_tiles * p.nphase;
   const int kb_per_tap = p.Cin / BK;
+  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : kChunkKB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -187,18 +188,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     int stage = 0;
     uint32_t phase = 0;
     uint32_t chunk = 0;     // running chunk counter of this CTA -> accumulator ring slot
-    for (int tile = sched_id; tile < num_tiles; tile += nsched) {
-      int ph_m, mn_m;
-      decode_tile(tile, p.nphase, nsched, ph_m, mn_m);
-      const int num_kb = p.ph_ntaps[ph_m] * kb_per_tap;
-      if (lane == 0 && leader) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
+    // All 32 lanes run this loop with warp-uniform values so that descriptors live in uniform
+    // registers; one elected lane issues the tcgen05 instructions.  (Under a divergent
+    // `if (lane == 0)` the compiler wraps every MMA in an ELECT / R2UR.BROADCAST waterfall loop,
+    // which makes the single issuing thread the bottleneck: 12 MMAs of 75 cycles per k-block.)
+    if (leader) {
+      for (int tile = sched_id; tile < num_tiles; tile += nsched) {
+        int ph_m, mn_m;
+        decode_tile(tile, p.nphase, nsched, ph_m, mn_m);
+        const int num_kb = p.ph_ntaps[ph_m] * kb_per_tap;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++chunk) {
           const int as = chunk % kNumAcc;
           const uint32_t aphase = (chunk / kNumAcc) & 1u;
           mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + as * kAccCols;
-          const int kb_end = (kb0 + kChunkKB < num_kb) ? kb0 + kChunkKB : num_kb;
+          const int kb_end = (kb0 + chunk_kb < num_kb) ? kb0 + chunk_kb : num_kb;
           for (int kb = kb0; kb < kb_end; ++kb) {
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
@@ -208,29 +213,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint64_t db_hi = make_smem_desc(sa + 2 * S::kABytes, 16, 1024, kSwizzle128B);
             const uint64_t db_lo =
                 make_smem_desc(sa + 2 * S::kABytes + S::kBBytes, 16, 1024, kSwizzle128B);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
-              // smallest terms first, then the dominant hi*hi product
-              if constexpr (CG == 2) {
-                umma_bf16_cg2(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
-                umma_bf16_cg2(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-                umma_bf16_cg2(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
-              } else {
-                umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
-                umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-                umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 2) >> 4);
+                // smallest terms first, then the dominant hi*hi product
+                if constexpr (CG == 2) {
+                  umma_bf16_cg2(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                  umma_bf16_cg2(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                  umma_bf16_cg2(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+                } else {
+                  umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                  umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                  umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
+              }
+              if constexpr (CG == 2) umma_commit_cg2_mc(&bars->empty[stage]);
+              else umma_commit(&bars->empty[stage]);
+              if (kb + 1 == kb_end) {
+                if constexpr (CG == 2) umma_commit_cg2_mc(&bars->tmem_full[as]);
+                else umma_commit(&bars->tmem_full[as]);
               }
             }
-            if constexpr (CG == 2) umma_commit_cg2_mc(&bars->empty[stage]);
-            else umma_commit(&bars->empty[stage]);
+            __syncwarp();
             if (++stage == kSt) { stage = 0; phase ^= 1u; }
           }
-          if constexpr (CG == 2) umma_commit_cg2_mc(&bars->tmem_full[as]);
-          else umma_commit(&bars->tmem_full[as]);
         }
       }
-      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
@@ -263,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
 
-      for (int kb0 = 0; kb0 < num_kb; kb0 += kChunkKB, ++chunk) {
+      for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++chunk) {
         const int as = chunk % kNumAcc;
         const uint32_t aphase = (chunk / kNumAcc) & 1u;
         mbar_wait(&bars->tmem_full[as], aphase);
@@ -453,6 +462,7 @@ static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void
 // 0 = automatic (CTA pairs when the launch has at least one full wave of 256-row tiles),
 // 1 / 2 = forced (tests, RW_CONV_CG environment variable)
 static int g_conv_cg = -1;
+static int g_chunk_kb = 0;    // experiment hook: k-blocks per accumulation chunk
 
 int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
                    const void* w_lo, int wk_total, cudaStream_t stream) {
@@ -470,6 +480,8 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
   if (g_conv_cg < 0) {
     const char* e = getenv("RW_CONV_CG");
     g_conv_cg = e ? atoi(e) : 0;
+    const char* c = getenv("RW_CHUNK_KB");
+    g_chunk_kb = c ? atoi(c) : 0;
   }
   int cg = g_conv_cg;
   if (cg != 1 && cg != 2) {
@@ -478,8 +490,10 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
     const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
     cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
   }
-  if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
-  return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  ConvTcParams q = p;
+  if (g_chunk_kb > 0) q.chunk_kb = g_chunk_kb;
+  if (cg == 2) return conv_tc_launch_cg<2>(q, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  return conv_tc_launch_cg<1>(q, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
 }
 
 }  // namespace rw

@@ -135,7 +135,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(TM, TN, 1, 1);
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (descriptors stay in uniform registers)
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk = 0;
@@ -157,21 +158,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
               make_smem_desc(sa + 2 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
           const uint64_t db_lo =
               make_smem_desc(sa + 3 * kPlaneBytes, lbo_bytes, sbo_bytes, kSwizzle128B);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < RB / UMMA_K; ++kk) {
-            // 16 rows = two 8-row swizzle groups of 1024 B
-            const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 128) >> 4);
-            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((i - i0) | kk) != 0);
-            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+            for (int kk = 0; kk < RB / UMMA_K; ++kk) {
+              // 16 rows = two 8-row swizzle groups of 1024 B
+              const uint64_t adv = static_cast<uint64_t>((kk * UMMA_K * 128) >> 4);
+              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((i - i0) | kk) != 0);
+              umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+            umma_commit(&bars->empty[stage]);
+            if (i + 1 == i_end) umma_commit(&bars->tmem_full[as]);
           }
-          umma_commit(&bars->empty[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->tmem_full[as]);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;

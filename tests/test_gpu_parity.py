@@ -239,6 +239,7 @@ def test_generator_pixels_vs_golden_and_oracle(cuda_model, seeded_sd, z40, golde
     with torch.no_grad():
         ref = orc.generator_forward(seeded_sd, z40[:2])
     err = (pix - ref).abs().max().item()
+    print('PIXEL_ERR max|d| = %.3e (pixel absmax %.1f)' % (err, ref.abs().max().item()))
     assert err < 1e-3, err
     # batch-size independence: noise row i depends only on (i, H*W), so image 0 of a batch of 2
     # equals the singleton batch

@@ -26,12 +26,14 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def main(B=32):
+def main(B=32, only=None):
     torch.manual_seed(0)
     kern = (torch.tensor([1., 3., 3., 1.])[:, None] * torch.tensor([1., 3., 3., 1.])[None, :])
     kern = (kern / kern.sum() * 4).cuda()
     out, tot_f, tot_fb, fl_f = [], 0.0, 0.0, 0.0
     for name, cin, cout, h, up in SHAPES:
+        if only and name not in only:
+            continue
         x = torch.randn(B, cin, h, h, device='cuda', requires_grad=True)
         style = (torch.randn(B, cin, device='cuda') * 0.5 + 1).requires_grad_(True)
         w = torch.nn.Parameter(torch.randn(1, cout, cin, 3, 3, device='cuda'))
@@ -70,4 +72,4 @@ def main(B=32):
 
 
 if __name__ == '__main__':
-    main()
+    main(only=set(sys.argv[1:]) or None)
