@@ -43,6 +43,8 @@ constexpr int kNumThreads = 192;
 // CHUNK of kChunkKB k-blocks (K=512: 96 accumulations); the epilogue warps add the chunks in
 // fp32 registers with round-to-nearest.  kNumAcc TMEM buffers form a ring between the MMA
 // issuer and the epilogue.
+// (kChunkKB must stay a compile-time constant: a run-time chunk bound cost 15 % in this kernel —
+//  measured chunk 8 -> pixel error 5.2e-4, chunk 16 -> 8.1e-4, >= 36 fails the 1e-3 bound)
 constexpr int kChunkKB = 8;
 // Measured (tools/cuda/mma_rate.cu, profiles/r1_mma_rate.txt): an M=128,K=16 bf16 MMA costs
 // 75 cycles for N <= 128 and 128 cycles for N = 256.  Issuing A_hi x [B_hi ; B_lo] as one N=256
@@ -117,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int mn_tiles = m_tiles * n_tiles;
   const int num_tiles = mn_tiles * p.nphase;
   const int kb_per_tap = p.Cin / BK;
-  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : kChunkKB;
+  constexpr int chunk_kb = kChunkKB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -462,7 +464,6 @@ static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void
 // 0 = automatic (CTA pairs when the launch has at least one full wave of 256-row tiles),
 // 1 / 2 = forced (tests, RW_CONV_CG environment variable)
 static int g_conv_cg = -1;
-static int g_chunk_kb = 0;    // experiment hook: k-blocks per accumulation chunk
 
 int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, const void* w_hi,
                    const void* w_lo, int wk_total, cudaStream_t stream) {
@@ -480,8 +481,6 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
   if (g_conv_cg < 0) {
     const char* e = getenv("RW_CONV_CG");
     g_conv_cg = e ? atoi(e) : 0;
-    const char* c = getenv("RW_CHUNK_KB");
-    g_chunk_kb = c ? atoi(c) : 0;
   }
   int cg = g_conv_cg;
   if (cg != 1 && cg != 2) {
@@ -490,10 +489,8 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
     const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
     cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
   }
-  ConvTcParams q = p;
-  if (g_chunk_kb > 0) q.chunk_kb = g_chunk_kb;
-  if (cg == 2) return conv_tc_launch_cg<2>(q, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
-  return conv_tc_launch_cg<1>(q, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
 }
 
 }  // namespace rw

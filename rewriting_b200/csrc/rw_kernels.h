@@ -40,7 +40,6 @@ struct ConvTcParams {
   // out_mode 0: strided (NCHW-like) store at valid positions only
   // out_mode 1: channels-last rows  out[(ph*rows + p)*Cout + o]  for every row p < rows
   int out_mode;
-  int chunk_kb;   // k-blocks per TMEM accumulation chunk (0 -> default 8), see conv_tc.cu
   // fused producer outputs (generation fast path): the NEXT layer's key planes
   //   next_{hi,lo}[p][o] = split_bf16(next_scale[b,o] * y)   (zero at pad positions)
   void* next_hi;
