@@ -91,7 +91,8 @@ int rw_modconv_up_fwd(const void* kp_hi, const void* kp_lo, const void* wt_hi, c
 /* ---- generation fast path: producers write the consumer's operands directly ----
  * rw_modconv_fwd_fused = rw_modconv_fwd whose epilogue can additionally emit
  *   next_{hi,lo}[rows][Cout] : key planes of the NEXT layer, split_bf16(next_scale[b,o] * y)
- *   rgb_part[Cout/128][B][3][H*W] : this layer's ToRGB partial sums with rgb_w[B,3,Cout]
+ *   rgb_part[Cout/64][B][3][H*W] : this layer's ToRGB partial sums (one per 64-channel group)
+ *                                   with rgb_w[B,3,Cout]
  * `out` (fp32 NCHW) becomes optional.  rw_modconv_up_fwd_cl writes the conv_transpose output
  * channels-last per phase, t_cl[4][rows][Cout]; rw_blur_up_fused turns it into the next layer's
  * planes (and/or fp32 NCHW); rw_rgb_combine = sum of partials + bias + 2x-upsampled skip. */

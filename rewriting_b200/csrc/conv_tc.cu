@@ -36,7 +36,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // bf16 elements per k-block = one 128B swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 3;
-constexpr int kNumThreads = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue: two warps per TMEM lane
+// quarter, each owning 64 of the tile's 128 columns (64 fp32 running sums per thread: no spills,
+// and twice the epilogue throughput for the short-K phase tiles of the upsampling layers)
+constexpr int kNumThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiCols = 64;
 // The tensor core's fp32 accumulate truncates (round-toward-zero) on every MMA: measured
 // relative bias ~ -2^-25 per accumulation (profiles/r1_precision_probe.json), i.e. 1.6e-5
 // after the 864 accumulations of a K=4608 tile.  So a TMEM accumulator only ever holds a
@@ -65,9 +70,9 @@ struct ConvSmem {
   static constexpr int kABytes = BM * BK * 2;          // one plane
   static constexpr int kBBytes = (BN / CG) * BK * 2;   // one plane (this CTA's share)
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  // per-epilogue-warp transpose scratch: 32 rows x (128 B + 16 B pad)
-  static constexpr int kScratchRow = 144;
-  static constexpr int kScratchBytes = 4 * 32 * kScratchRow;
+  // per-epilogue-warp transpose scratch: 32 rows x (64 B + 16 B pad)
+  static constexpr int kScratchRow = 80;
+  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchRow;
   static constexpr int kTotal = kStagesN * kStageBytes + kScratchBytes + 1024 /*align slack*/ +
                                 256 /*barriers*/;
 };
@@ -132,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     for (int s = 0; s < kNumAcc; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4 * CG);   // epilogue warps of every CTA of the pair
+      mbar_init(&bars->tmem_empty[s], kEpiWarps * CG);   // epilogue warps of every CTA of the pair
     }
     fence_mbar_init();
   }
@@ -245,15 +250,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which 64 of the tile's 128 columns
+    const int cbase = half * kEpiCols;
     const int img = p.Hp * p.Wp;
+    uint8_t* scr = scratch_base + (warp - 2) * 32 * S::kScratchRow;
     uint32_t chunk = 0;
     for (int tile = sched_id; tile < num_tiles; tile += nsched) {
       int ph, mn;
       decode_tile(tile, p.nphase, nsched, ph, mn);
       const int num_kb = p.ph_ntaps[ph] * kb_per_tap;
       const int Hv = p.ph_Hv[ph], Wv = p.ph_Wv[ph];
-      const int n0 = (mn % n_tiles) * BN;
+      const int n0 = (mn % n_tiles) * BN + cbase;          // first output channel of this warp
       const int m0 = (mn / n_tiles) * BM * CG + cta_rank * BM;
       const int prow = m0 + q * 32 + lane;
       const int b = prow / img;
@@ -261,18 +269,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       const int yy = rem / p.Wp;
       const int xx = rem - yy * p.Wp;
       const bool valid = (prow < p.rows) && (yy < Hv) && (xx < Wv);
-      float nz = 0.f;
-      if (valid && p.noise != nullptr) {
-        nz = __ldg(p.noise_w) * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
-                                      static_cast<size_t>(yy) * Wv + xx);
-      }
-      float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
-                    static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
-      const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
 
-      float acc[BN];
+      float acc[kEpiCols];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < kEpiCols; ++j) acc[j] = 0.f;
 
       for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++chunk) {
         const int as = chunk % kNumAcc;
@@ -280,9 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < kEpiCols; c0 += 32) {
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kAccCols + c0) +
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kAccCols + cbase + c0) +
                                  (static_cast<uint32_t>(q * 32) << 16);
           tmem_ld_32x32(taddr, v);
           tmem_ld_wait();
@@ -298,11 +298,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       }
 
       // ---- fused epilogue -------------------------------------------------------------
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-      const float* rw0 = p.rgb_w ? p.rgb_w + (static_cast<size_t>(b) * 3) * p.Cout : nullptr;
+      const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
       if (valid) {
+        float nz = 0.f;
+        if (p.noise != nullptr)
+          nz = __ldg(p.noise_w) * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
+                                        static_cast<size_t>(yy) * Wv + xx);
+        float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
+                      static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
+        const float* rw0 = p.rgb_w ? p.rgb_w + (static_cast<size_t>(b) * 3) * p.Cout : nullptr;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) {
+        for (int j = 0; j < kEpiCols; ++j) {
           const int o = n0 + j;
           float t = acc[j];
           if (scl) t *= __ldg(scl + o);
@@ -318,8 +325,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
         }
         if (rw0) {
+          // one partial per 64-channel group: rgb_part[(n_tile*2 + half)][b][c][y*Wv+x]
           const size_t hw = static_cast<size_t>(Hv) * Wv;
-          float* rp = p.rgb_part + ((static_cast<size_t>(mn % n_tiles) * p.B + b) * 3) * hw +
+          float* rp = p.rgb_part +
+                      ((static_cast<size_t>((mn % n_tiles) * 2 + half) * p.B + b) * 3) * hw +
                       static_cast<size_t>(yy) * Wv + xx;
           rp[0] = r0;
           rp[hw] = r1;
@@ -328,24 +337,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       } else if (p.out_mode == 1 && prow < p.rows && scl) {
         // channels-last raw rows are written for every row (pad rows are never read back)
 #pragma unroll
-        for (int j = 0; j < BN; ++j) acc[j] *= __ldg(scl + n0 + j);
+        for (int j = 0; j < kEpiCols; ++j) acc[j] *= __ldg(scl + n0 + j);
       }
       // Row-per-lane registers -> global through a warp-private smem transpose, so that every
-      // store instruction covers whole 128-byte lines (4 rows x 128 B) instead of 32 rows x 16 B.
-      uint8_t* scr = scratch_base + (warp - 2) * 32 * S::kScratchRow;
-      const int rr0 = lane >> 3;        // row within a group of 4
-      const int c16 = lane & 7;         // 16-byte column slot
+      // store instruction covers whole 64-byte row segments (8 rows x 64 B) instead of
+      // 32 rows x 16 B.
+      const int rr0 = lane >> 2;        // row within a group of 8
+      const int c16 = lane & 3;         // 16-byte column slot
       if (p.out != nullptr && p.out_mode == 1) {
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < kEpiCols; c0 += 16) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
+          for (int j4 = 0; j4 < 4; ++j4)
             *reinterpret_cast<float4*>(scr + lane * S::kScratchRow + j4 * 16) = make_float4(
                 acc[c0 + 4 * j4], acc[c0 + 4 * j4 + 1], acc[c0 + 4 * j4 + 2], acc[c0 + 4 * j4 + 3]);
           __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rr0;
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + rr0;
             const int grow = m0 + q * 32 + rr;
             const float4 v = *reinterpret_cast<const float4*>(scr + rr * S::kScratchRow + c16 * 16);
             if (grow < p.rows)
@@ -358,15 +367,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       if (p.next_hi != nullptr) {
         const float* ns = p.next_scale + static_cast<size_t>(valid ? b : 0) * p.Cout + n0;
 #pragma unroll
-        for (int half = 0; half < BN / 64; ++half) {
+        for (int part = 0; part < kEpiCols / 32; ++part) {      // 32 channels = 64 B per pass
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
 #pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
+            for (int j8 = 0; j8 < 4; ++j8) {
               uint32_t w[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int j = half * 64 + j8 * 8 + 2 * e;
+                const int j = part * 32 + j8 * 8 + 2 * e;
                 const float k0 = valid ? __ldg(ns + j) * acc[j] : 0.f;
                 const float k1 = valid ? __ldg(ns + j + 1) * acc[j + 1] : 0.f;
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(k0, k1);
@@ -384,12 +393,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             __syncwarp();
             __nv_bfloat16* dstp = static_cast<__nv_bfloat16*>(plane == 0 ? p.next_hi : p.next_lo);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rr0;
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + rr0;
               const int grow = m0 + q * 32 + rr;
               const uint4 v = *reinterpret_cast<const uint4*>(scr + rr * S::kScratchRow + c16 * 16);
               if (grow < p.rows)
-                *reinterpret_cast<uint4*>(dstp + static_cast<size_t>(grow) * p.Cout + n0 + half * 64 +
+                *reinterpret_cast<uint4*>(dstp + static_cast<size_t>(grow) * p.Cout + n0 + part * 32 +
                                           c16 * 8) = v;
             }
             __syncwarp();

@@ -159,7 +159,7 @@ def forward(model, z, upto_key_layer=None):
                 nh = torch.empty((rows, Cout), dtype=torch.bfloat16, device=dev)
                 nl = torch.empty_like(nh)
             rgb_w = rgb_part = None
-            ntile = Cout // 128
+            ntile = Cout // 64          # one ToRGB partial per 64-channel epilogue group
             if rgb is not None:
                 s_rgb = rgb_styles[num]                                          # [B, Cout]
                 w3 = rgb.conv.weight.detach().reshape(3, Cout) * (1.0 / math.sqrt(Cout))
