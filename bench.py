@@ -234,7 +234,6 @@ def main():
     from rewriting_b200 import dist as rdist
     _cabi.load()
     model = build_model(device)
-    gfl = conv_gflop_layers()
 
     # per-rank z shard (weak scaling: every rank gets its own K+W batches of 32)
     n_batches = W + K

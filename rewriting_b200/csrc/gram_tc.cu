@@ -61,7 +61,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int lane = threadIdx.x & 31;
 
   // tile decode (optionally upper-triangular tiles only)
-  const int mt_count = p.Cm / TM;
   const int nt_count = p.Cn / TN;
   int mt, nt;
   if (p.upper_only) {

@@ -26,12 +26,10 @@ What is different here is where the arithmetic runs:
 """
 import copy
 import ctypes
-import json  # noqa: F401  (kept: callers import it through this module in notebooks)
 import os
 import random
+import re as _re
 import time
-import warnings
-from collections import OrderedDict  # noqa: F401
 
 import torch
 
@@ -43,7 +41,6 @@ from ..utils.stylegan2 import models as sg2
 (all_obs, all_weight, all_CinvK, all_kCinvK, e_val, e_vec, kbasis, row_dirs, q) = (None,) * 9
 
 FUSED_CHUNK = 64     # iterations per fused launch when a callback wants per-step losses
-import re as _re
 _DCONV_RE = _re.compile(r'^layer(\d+)\.(?:sconv|conv)\.mconv\.dconv$')
 
 

@@ -1,46 +1,57 @@
 """StyleGAN2 (sequential form) on the rewriting_b200 kernels.
 
-Mirror of the reference's `utils/stylegan2/__init__.py:39-47`: `load_seq_stylegan(category,
-truncation, **kw)` builds a `SeqStyleGAN2` and loads rosinality-format weights.  The
-reference downloads from rewriting.csail.mit.edu; pass `path=` (or set
-REWRITING_B200_WEIGHTS to a directory holding the same file names) to load from disk — the
-download is attempted only if neither is given.
+`load_seq_stylegan(category, truncation=1.0, **kw)` mirrors the reference entry point
+(utils/stylegan2/__init__.py:39-47 there): build a `SeqStyleGAN2` of the right resolution for
+`category`, load rosinality-format weights (`{'g_ema': ..., 'latent_avg': ...}`), move it to the
+GPU.  Weight files keep the reference's names (`stylegan2_<category>-<hash>.pt`); they are read
+from `path=`, from the directory in $REWRITING_B200_WEIGHTS, or — last resort, needs network —
+fetched from the reference's server.
 """
 import os
-from collections import defaultdict
 
 import torch
 
-from .models import SeqStyleGAN2, DataBag
+from .models import SeqStyleGAN2, DataBag  # noqa: F401
 
 WEIGHT_URLS = 'http://rewriting.csail.mit.edu/data/models/'
-sizes = defaultdict(lambda: 256, faces=1024, car=512)
 
-FILENAMES = dict(
-    bedroom='stylegan2_bedroom-6fa55a6e.pt',
-    car='stylegan2_car-3659b4b6.pt',
-    cat='stylegan2_cat-d8dc98b2.pt',
-    church='stylegan2_church-e8ca9fd0.pt',
-    faces='stylegan2_faces-2858cc2e.pt',
-    horse='stylegan2_horse-499b5380.pt',
-    kitchen='stylegan2_kitchen-b3a526e9.pt',
-    places='stylegan2_places-a3b72d71.pt',
-)
+# category -> content hash of the published checkpoint
+_HASHES = {
+    'bedroom': '6fa55a6e', 'car': '3659b4b6', 'cat': 'd8dc98b2', 'church': 'e8ca9fd0',
+    'faces': '2858cc2e', 'horse': '499b5380', 'kitchen': 'b3a526e9', 'places': 'a3b72d71',
+}
+FILENAMES = {cat: 'stylegan2_%s-%s.pt' % (cat, h) for cat, h in _HASHES.items()}
+
+
+class _Sizes(dict):
+    """output resolution per category (256 unless listed)"""
+
+    def __missing__(self, key):
+        return 256
+
+
+sizes = _Sizes(faces=1024, car=512)
+
+
+def _checkpoint_source(category, path):
+    if path is not None:
+        return path, True
+    root = os.environ.get('REWRITING_B200_WEIGHTS')
+    if root:
+        return os.path.join(root, FILENAMES[category]), True
+    return WEIGHT_URLS + FILENAMES[category], False
 
 
 def load_state_dict(category, path=None):
-    fn = FILENAMES[category]
-    if path is None and os.environ.get('REWRITING_B200_WEIGHTS'):
-        path = os.path.join(os.environ['REWRITING_B200_WEIGHTS'], fn)
-    if path is not None:
-        return torch.load(path, map_location='cpu')
-    return torch.hub.load_state_dict_from_url(WEIGHT_URLS + fn, map_location='cpu')
+    src, local = _checkpoint_source(category, path)
+    if local:
+        return torch.load(src, map_location='cpu')
+    return torch.hub.load_state_dict_from_url(src, map_location='cpu')
 
 
 def load_seq_stylegan(category, truncation=1.0, path=None, **kwargs):
-    """Loads the nn.Sequential StyleGAN2 for `category` and puts it on the GPU."""
-    state_dict = load_state_dict(category, path=path)
-    g = SeqStyleGAN2(sizes[category], style_dim=512, n_mlp=8, truncation=truncation, **kwargs)
-    g.load_state_dict(state_dict['g_ema'], latent_avg=state_dict['latent_avg'])
-    g.cuda()
-    return g
+    """The nn.Sequential StyleGAN2 for `category`, weights loaded, on the GPU."""
+    ckpt = load_state_dict(category, path=path)
+    net = SeqStyleGAN2(sizes[category], style_dim=512, n_mlp=8, truncation=truncation, **kwargs)
+    net.load_state_dict(ckpt['g_ema'], latent_avg=ckpt['latent_avg'])
+    return net.cuda()
