@@ -478,3 +478,20 @@ def test_zero_linear_insert_and_erase_run_on_the_kernels(cuda_model, z40, golden
                    niter=11, piter=10)
     moved = (gw.target_weights().detach() - W0).abs().max().item()
     assert 1e-3 < moved < 1.0 and torch.isfinite(gw.target_weights()).all()
+
+
+def test_bulk_sampling_matches_reference_seed_rule(cuda_model, seeded_sd):
+    """config 5: batch j is generated from zdataset seed batch*j (utils/get_samples.py:121-124)."""
+    from rewriting_b200 import sampling
+    from rewriting_b200.utils import zdataset
+    imgs, idx = sampling.get_samples(cuda_model, nimgs=4, batch=2)       # 4//2+1 = 3 batches
+    assert idx == [0, 1, 2] and imgs.shape == (6, 3, 256, 256) and imgs.dtype == torch.float32
+    z1 = zdataset.standard_z_sample(2, 512, seed=2)
+    assert torch.equal(sampling.z_for_batch(1, 2), z1)
+    with torch.no_grad():
+        ref = orc.generator_forward(seeded_sd, z1)
+    assert (imgs[2:4] - ref).abs().max().item() < 1e-3
+    u8, _ = sampling.get_samples(cuda_model, nimgs=2, batch=2, out_dtype=torch.uint8,
+                                 reference_count=False)
+    want = (imgs[0:2] * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)
+    assert u8.shape == (2, 3, 256, 256) and (u8.int() - want.int()).abs().max().item() <= 1
