@@ -114,6 +114,21 @@ int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const fl
 int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int n,
               const float* const* w, const float* const* bias, float* const* out, const int* lat,
               const int* chans, rw_stream_t stream);
+/* EqualLinear (utils/stylegan2/models.py:487-511): out[b,c] = sum_k x[b,k]*(w[c,k]*scale) +
+ * bias[c]*bias_mul, then lrelu(0.2)*sqrt(2) when act != 0 (the mapping network's
+ * fused_lrelu layers, lr_mul = 0.01).  One launch per layer instead of sgemm + bias_act + two
+ * elementwise kernels. */
+int rw_equal_linear(const float* x, int B, int K, const float* w, const float* bias, int Cout,
+                    float scale, float bias_mul, int act, float* out, rw_stream_t stream);
+/* PixelNormL (models.py:609-614): out = z * rsqrt(mean(z^2, dim 1) + 1e-8), z [B,K] */
+int rw_pixel_norm(const float* z, int B, int K, float* out, rw_stream_t stream);
+/* Everything that depends only on the styles, for all layers in one launch (n <= 32 jobs):
+ * kind 0: out[b,o] = rsqrt(sum_i style[b,i]^2 * w[o,i] + eps)  (w = wsq of rw_prep_weights; the
+ *         demodulation factor of models.py:325-327);
+ * kind 1: out[b,c,i] = (wscale*w[c,i])*style[b,i]  (ToRGB's modulated 1x1 weights, cout = 3). */
+int rw_demod_multi(int B, float eps, int n, const float* const* style, const float* const* w,
+                   float* const* out, const int* cout, const int* cin, const int* kind,
+                   const float* wscale, rw_stream_t stream);
 int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
                    const float* prev, const float* kernel4x4, float* out, rw_stream_t stream);
 /* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */
@@ -158,6 +173,36 @@ int rw_modconv_up_dgrad(const void* gph_hi, const void* gph_lo, const void* wt_h
 int rw_conv_up_wgrad(const void* gph_hi, const void* gph_lo, const void* kp_hi, const void* kp_lo,
                      long long rows, int Cout, int Cin, int Wp, float* dw_toi, void* workspace,
                      size_t workspace_bytes, rw_stream_t stream);
+
+/* ---- StyledConv backward: the HBM-bound passes between the tensor-core kernels ----
+ * (autograd of FusedLeakyReLUF / NoiseInjectionF / BlurF / ApplyStyle / the demodulation:
+ *  utils/stylegan2/op/fused_act.py:19-86, utils/stylegan2/models.py:275-281,320-328,535-546,616-620)
+ *
+ * rw_act_grad_reduce: one pass over (gy, y) of a [B,C,HW] layer output y = act(t + nw*noise + bias):
+ *   g_pre = dL/d(pre-activation) (written unless g_pre == NULL; equal to gy when act == 0),
+ *   s_sum[b,c] = sum_p g_pre, s_dot[b,c] = sum_p g_pre*t (t recovered from y), s_noise[b,c] =
+ *   sum_p g_pre*noise[b,p].  noise / bias may be NULL.
+ * rw_blur_adj_phase_keys: gradient phase planes [rows][4*C] (the layout of rw_prep_phase_keys) of
+ *   scale[b,c] * blur^T(g_pre), g_pre [B,C,2H,2W]; the [B,C,2H+1,2W+1] tensor is never stored.
+ * rw_dgrad_finish: gs_raw[b,i] = sum_p dk*x; dk <- dk*style[b,i] in place ([B,C,HW] planes).
+ * rw_wgrad_finish: gw[o,i,tap] = scale*dw_toi[o,tap,i] - scale^2*w[o,i,tap]*sum_b s_dot[b,o]*
+ *   demod[b,o]^2*style[b,i]^2 (s_dot == NULL: no demodulation term).
+ * rw_style_grad_finish: g_style[b,i] = gs_raw[b,i] - style[b,i]*sum_o s_dot[b,o]*demod[b,o]^2*
+ *   wsq[o,i] (gs_raw == NULL: 0). */
+int rw_act_grad_reduce(const float* gy, const float* y, const float* noise,
+                       long long noise_bstride, const float* noise_w, const float* bias, int act,
+                       int B, int C, int HW, float* g_pre, float* s_sum, float* s_dot,
+                       float* s_noise, rw_stream_t stream);
+int rw_blur_adj_phase_keys(const float* g_pre, const float* scale_bc, const float* kernel4x4, int B,
+                           int C, int H, int W, void* hi, void* lo, rw_stream_t stream);
+int rw_dgrad_finish(float* dk, const float* x, const float* style, int B, int C, int HW,
+                    float* gs_raw, rw_stream_t stream);
+int rw_wgrad_finish(const float* dw_toi, const float* w, const float* s_dot, const float* demod,
+                    const float* style, int B, int Cout, int Cin, float scale, float* gw,
+                    rw_stream_t stream);
+int rw_style_grad_finish(const float* gs_raw, const float* style, const float* s_dot,
+                         const float* demod, const float* wsq, int B, int Cout, int Cin,
+                         float* g_style, rw_stream_t stream);
 
 /* ---- rank-r edit ---- */
 /* out = base + sign * P_d(w);  P_d(w)[o,:,t] = sum_r (w[o,:,t] . d_r) d_r;  base may be NULL */

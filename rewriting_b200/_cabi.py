@@ -57,6 +57,9 @@ SIGNATURES = {
     'rw_blur_up_fused': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                  c_int, c_p, c_p, c_p, c_p, c_p]),
     'rw_styles': (c_int, [c_p, c_int, c_int, c_int, c_f, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'rw_equal_linear': (c_int, [c_p, c_int, c_int, c_p, c_p, c_int, c_f, c_f, c_int, c_p, c_p]),
+    'rw_pixel_norm': (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    'rw_demod_multi': (c_int, [c_int, c_f, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     'rw_rgb_combine': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
     'rw_blur_up_act': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                c_int, c_p, c_p]),
@@ -75,6 +78,12 @@ SIGNATURES = {
                                     c_p, c_p]),
     'rw_conv_up_wgrad': (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_int, c_int, c_p, c_p, c_sz,
                                  c_p]),
+    'rw_act_grad_reduce': (c_int, [c_p, c_p, c_p, c_ll, c_p, c_p, c_int, c_int, c_int, c_int,
+                                   c_p, c_p, c_p, c_p, c_p]),
+    'rw_blur_adj_phase_keys': (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
+    'rw_dgrad_finish': (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
+    'rw_wgrad_finish': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p]),
+    'rw_style_grad_finish': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     'rw_project_rank': (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_p, c_p]),
     'rw_insert_loop': (c_int, [ctypes.POINTER(InsertArgs), c_p]),
     'rw_debug_rowgemm': (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),

@@ -338,7 +338,35 @@ int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int 
     set_last_error("rw_styles: bad argument");
     return RW_ERR_BAD_ARG;
   }
-  return styles_launch(latent, B, n_latent, K, scale, n, w, bias, out, lat, chans, stream);
+  return styles_launch(latent, B, n_latent, K, scale, 1.f, 0, n, w, bias, out, lat, chans, stream);
+}
+
+int rw_equal_linear(const float* x, int B, int K, const float* w, const float* bias, int Cout,
+                    float scale, float bias_mul, int act, float* out, rw_stream_t stream) {
+  if (!x || !w || !bias || !out || B < 1 || K < 1 || Cout < 1) {
+    set_last_error("rw_equal_linear: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  const int lat = 0;
+  return styles_launch(x, B, 1, K, scale, bias_mul, act, 1, &w, &bias, &out, &lat, &Cout, stream);
+}
+
+int rw_pixel_norm(const float* z, int B, int K, float* out, rw_stream_t stream) {
+  if (!z || !out || B < 1 || K < 1) {
+    set_last_error("rw_pixel_norm: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return pixel_norm_launch(z, B, K, out, stream);
+}
+
+int rw_demod_multi(int B, float eps, int n, const float* const* style, const float* const* w,
+                   float* const* out, const int* cout, const int* cin, const int* kind,
+                   const float* wscale, rw_stream_t stream) {
+  if (!style || !w || !out || !cout || !cin || !kind || !wscale || B < 1) {
+    set_last_error("rw_demod_multi: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return demod_multi_launch(B, eps, n, style, w, out, cout, cin, kind, wscale, stream);
 }
 
 int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
@@ -548,6 +576,57 @@ int rw_conv_up_wgrad(const void* gph_hi, const void* gph_lo, const void* kp_hi, 
   if (rc) return rc;
   return reduce_partials_launch(p.partial, p.splits, Cout, 9 * Cin, p.ldp, dw_toi, 9LL * Cin, 0, 0,
                                 stream);
+}
+
+int rw_act_grad_reduce(const float* gy, const float* y, const float* noise,
+                       long long noise_bstride, const float* noise_w, const float* bias, int act,
+                       int B, int C, int HW, float* g_pre, float* s_sum, float* s_dot,
+                       float* s_noise, rw_stream_t stream) {
+  if (!gy || !y || !s_sum || !s_dot || !s_noise || B < 0 || C < 1 || HW < 0 ||
+      (noise && !noise_w)) {
+    set_last_error("rw_act_grad_reduce: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return act_grad_reduce_launch(gy, y, noise, noise_bstride, noise_w, bias, act, B, C, HW, g_pre,
+                                s_sum, s_dot, s_noise, stream);
+}
+
+int rw_blur_adj_phase_keys(const float* g_pre, const float* scale_bc, const float* kernel4x4, int B,
+                           int C, int H, int W, void* hi, void* lo, rw_stream_t stream) {
+  if (!g_pre || !kernel4x4 || !hi || !lo || B < 1 || H < 1 || W < 1) {
+    set_last_error("rw_blur_adj_phase_keys: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return blur_adj_phase_launch(g_pre, scale_bc, kernel4x4, B, C, H, W, hi, lo, stream);
+}
+
+int rw_dgrad_finish(float* dk, const float* x, const float* style, int B, int C, int HW,
+                    float* gs_raw, rw_stream_t stream) {
+  if (!dk || !x || !style || !gs_raw || B < 0 || C < 1 || HW < 0) {
+    set_last_error("rw_dgrad_finish: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return dgrad_finish_launch(dk, x, style, B, C, HW, gs_raw, stream);
+}
+
+int rw_wgrad_finish(const float* dw_toi, const float* w, const float* s_dot, const float* demod,
+                    const float* style, int B, int Cout, int Cin, float scale, float* gw,
+                    rw_stream_t stream) {
+  if (!dw_toi || !w || !gw || Cout < 1 || Cin < 1 || (s_dot && (!demod || !style || B < 1))) {
+    set_last_error("rw_wgrad_finish: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return wgrad_finish_launch(dw_toi, w, s_dot, demod, style, B, Cout, Cin, scale, gw, stream);
+}
+
+int rw_style_grad_finish(const float* gs_raw, const float* style, const float* s_dot,
+                         const float* demod, const float* wsq, int B, int Cout, int Cin,
+                         float* g_style, rw_stream_t stream) {
+  if (!style || !g_style || B < 1 || Cin < 1 || (s_dot && (!demod || !wsq || Cout < 1))) {
+    set_last_error("rw_style_grad_finish: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return style_grad_finish_launch(gs_raw, style, s_dot, demod, wsq, B, Cout, Cin, g_style, stream);
 }
 
 int rw_project_rank(const float* w, const float* base, const float* d, int rank, int Cout,

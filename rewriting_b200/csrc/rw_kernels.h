@@ -104,9 +104,14 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
                          void* next_lo, float* y_out, cudaStream_t stream);
 int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
                        const float* prev, const float* k4, float* out, cudaStream_t stream);
-int styles_launch(const float* latent, int B, int n_latent, int K, float scale, int n,
-                  const float* const* w, const float* const* bias, float* const* out,
-                  const int* lat, const int* chans, cudaStream_t stream);
+int styles_launch(const float* latent, int B, int n_latent, int K, float scale, float bias_mul,
+                  int act, int n, const float* const* w, const float* const* bias,
+                  float* const* out, const int* lat, const int* chans, cudaStream_t stream);
+int pixel_norm_launch(const float* z, int B, int K, float* out, cudaStream_t stream);
+int demod_multi_launch(int B, float eps, int n, const float* const* style,
+                       const float* const* wsq, float* const* out, const int* cout,
+                       const int* cin, const int* kind, const float* wscale,
+                       cudaStream_t stream);
 int upfirdn2d_launch(const float* in, const float* kernel, int major, int in_h, int in_w, int kh,
                      int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
                      int py1, float* out, int out_h, int out_w, cudaStream_t stream);
@@ -118,6 +123,22 @@ int torgb_launch(const float* x, const float* style, const float* w, const float
                  cudaStream_t stream);
 int add_noise_launch(const float* x, const float* noise, long long noise_bstride, const float* noise_w,
                      int B, int C, int HW, float* y, cudaStream_t stream);
+
+// StyledConv backward, HBM-bound passes (bwd.cu)
+int act_grad_reduce_launch(const float* gy, const float* y, const float* noise,
+                           long long noise_bstride, const float* noise_w, const float* bias,
+                           int act, int B, int C, int HW, float* g_pre, float* s_sum,
+                           float* s_dot, float* s_noise, cudaStream_t stream);
+int blur_adj_phase_launch(const float* g_pre, const float* scale_bc, const float* k4, int B, int C,
+                          int H, int W, void* hi, void* lo, cudaStream_t stream);
+int dgrad_finish_launch(float* dk, const float* x, const float* style, int B, int C, int HW,
+                        float* gs_raw, cudaStream_t stream);
+int wgrad_finish_launch(const float* dwt, const float* w, const float* s_dot, const float* dm,
+                        const float* style, int B, int Cout, int Cin, float sc, float* gw,
+                        cudaStream_t stream);
+int style_grad_finish_launch(const float* gs_raw, const float* style, const float* s_dot,
+                             const float* dm, const float* wsq, int B, int Cout, int Cin,
+                             float* g_style, cudaStream_t stream);
 
 // rewrite (rewrite.cu)
 int project_rank_launch_signed(const float* w, const float* base, const float* d, int rank,

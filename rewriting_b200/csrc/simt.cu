@@ -6,6 +6,8 @@
 // Reference semantics (cited per kernel) are utils/stylegan2/models.py and
 // utils/stylegan2/op/*.  All kernels are coalesced / vectorised; none uses
 // tensor cores (these are byte-movement bound).
+#include <cstdlib>
+
 #include "rw_common.cuh"
 #include "rw_kernels.h"
 
@@ -483,6 +485,173 @@ blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
 }
 
 // ---------------------------------------------------------------------------
+// blur_up_pipe: the same arithmetic as blur_up_fused, restructured for memory-level parallelism.
+// The one-tile-per-CTA kernel above serialises  load -> sync -> FIR -> store  inside a CTA, and
+// at 4 CTAs/SM too few loads are in flight for HBM (measured 2.6 TB/s).  Here CTAs are
+// persistent (2 per SM), walk the tile list with a static stride and prefetch tile i+1 with
+// cp.async (16 B, L2 only, zero-fill outside the image) into the second shared-memory buffer
+// while tile i is filtered: 53.5 KB per CTA are always in flight.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const uint32_t nbytes = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nbytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct BlurTile {
+  int b, c0, ox0, oy0;
+};
+
+__device__ __forceinline__ BlurTile blur_tile(long long t, int tiles_x, int tiles_y, int cblocks) {
+  BlurTile r;
+  const int bx = static_cast<int>(t % tiles_x);
+  const long long q = t / tiles_x;
+  const int by = static_cast<int>(q % tiles_y);
+  const int bz = static_cast<int>(q / tiles_y);
+  r.b = bz / cblocks;
+  r.c0 = (bz - r.b * cblocks) * BF_C;
+  r.ox0 = bx * BF_TX;
+  r.oy0 = by * BF_TY;
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 2)
+blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
+                    const float* __restrict__ k4, const float* __restrict__ noise,
+                    long long noise_bstride, const float* __restrict__ noise_w,
+                    const float* __restrict__ bias, int act,
+                    const float* __restrict__ next_scale, __nv_bfloat16* __restrict__ next_hi,
+                    __nv_bfloat16* __restrict__ next_lo, float* __restrict__ y_out,
+                    int tiles_x, int tiles_y, long long ntiles) {
+  extern __shared__ float4 tile4[];      // 2 x [BF_PH*BF_PW][16 quads]
+  __shared__ float kf[16];
+  constexpr int TILE_ELEMS = BF_PH * BF_PW * 16;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int Hp_in = H + 1, Wp_in = W + 1;
+  const long long rows_in = static_cast<long long>(B) * Hp_in * Wp_in;
+  const int cblocks = C / BF_C;
+  const int tid = threadIdx.x;
+  if (tid < 16) kf[tid] = __ldg(k4 + 15 - tid);   // flipped kernel (upfirdn2d correlates)
+  const uint32_t smem0 = smem_u32(tile4);
+
+  auto issue = [&](long long t, int buf) {
+    const BlurTile bt = blur_tile(t, tiles_x, tiles_y, cblocks);
+    const uint32_t dst0 = smem0 + static_cast<uint32_t>(buf) * TILE_ELEMS * 16u;
+    for (int i = tid; i < TILE_ELEMS; i += 256) {
+      const int qd = i & 15;
+      const int pos = i >> 4;
+      const int ly = pos / BF_PW, lx = pos - ly * BF_PW;
+      const int ty = bt.oy0 + ly - 1, tx = bt.ox0 + lx - 1;
+      const bool valid = (ty >= 0 && ty <= Ho && tx >= 0 && tx <= Wo);
+      const float* src = t_cl;
+      if (valid) {
+        const int ph = (ty & 1) * 2 + (tx & 1);
+        const long long row = (static_cast<long long>(bt.b) * Hp_in + (ty >> 1)) * Wp_in + (tx >> 1);
+        src = t_cl + (ph * rows_in + row) * C + bt.c0 + qd * 4;
+      }
+      cp_async16_zfill(dst0 + static_cast<uint32_t>(i) * 16u, src, valid);
+    }
+    cp_async_commit();
+  };
+
+  long long t = blockIdx.x;
+  if (t < ntiles) issue(t, 0);
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  const int qd = tid & 15;
+  const int grp = tid >> 4;                 // 16 groups of 8 pixels
+  const int ly = grp >> 1;
+  const int lx0 = (grp & 1) * 8;
+  int buf = 0;
+  for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+    const long long tn = t + gridDim.x;
+    if (tn < ntiles) {
+      issue(tn, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                         // tile t landed for every thread (and kf on pass 0)
+    const BlurTile bt = blur_tile(t, tiles_x, tiles_y, cblocks);
+    const float4* tl = tile4 + buf * TILE_ELEMS;
+    const int oy = bt.oy0 + ly;
+    if (oy <= Ho) {
+      const int b = bt.b;
+      const int c = bt.c0 + qd * 4;
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (next_scale) sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
+      const size_t out_row0 = (static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1);
+      float4 a[8];
+#pragma unroll
+      for (int px = 0; px < 8; ++px) a[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int fy = 0; fy < 4; ++fy) {
+        float4 tv[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) tv[i] = tl[((ly + fy) * BF_PW + lx0 + i) * 16 + qd];
+#pragma unroll
+        for (int fx = 0; fx < 4; ++fx) {
+          const float kk = kf[fy * 4 + fx];
+#pragma unroll
+          for (int px = 0; px < 8; ++px) {
+            a[px].x = fmaf(tv[px + fx].x, kk, a[px].x);
+            a[px].y = fmaf(tv[px + fx].y, kk, a[px].y);
+            a[px].z = fmaf(tv[px + fx].z, kk, a[px].z);
+            a[px].w = fmaf(tv[px + fx].w, kk, a[px].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int px = 0; px < 8; ++px) {
+        const int ox = bt.ox0 + lx0 + px;
+        if (ox > Wo) break;
+        float4 v = a[px];
+        const bool real = (oy < Ho) && (ox < Wo);
+        if (real) {
+          if (noise) {
+            const float nz = nw * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
+                                        static_cast<size_t>(oy) * Wo + ox);
+            v.x += nz; v.y += nz; v.z += nz; v.w += nz;
+          }
+          v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
+          if (act) {
+            v.x = (v.x > 0.f ? v.x : 0.2f * v.x) * 1.4142135623730951f;
+            v.y = (v.y > 0.f ? v.y : 0.2f * v.y) * 1.4142135623730951f;
+            v.z = (v.z > 0.f ? v.z : 0.2f * v.z) * 1.4142135623730951f;
+            v.w = (v.w > 0.f ? v.w : 0.2f * v.w) * 1.4142135623730951f;
+          }
+          if (y_out) {
+            const size_t hw = static_cast<size_t>(Ho) * Wo;
+            float* yp = y_out + (static_cast<size_t>(b) * C + c) * hw + static_cast<size_t>(oy) * Wo + ox;
+            yp[0] = v.x; yp[hw] = v.y; yp[2 * hw] = v.z; yp[3 * hw] = v.w;
+          }
+        }
+        if (next_hi) {
+          const float k0 = real ? sc.x * v.x : 0.f, k1 = real ? sc.y * v.y : 0.f;
+          const float k2 = real ? sc.z * v.z : 0.f, k3 = real ? sc.w * v.w : 0.f;
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(k0, k1), h23 = __floats2bfloat162_rn(k2, k3);
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(k0 - f01.x, k1 - f01.y);
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(k2 - f23.x, k3 - f23.y);
+          const size_t off = (out_row0 + ox) * C + c;
+          *reinterpret_cast<uint2*>(next_hi + off) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(next_lo + off) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        }
+      }
+    }
+    __syncthreads();                         // buffer `buf` is free for the prefetch of pass +1
+  }
+}
+
+// ---------------------------------------------------------------------------
 // rgb_combine: out[b,c,y,x] = sum_nt part[nt][b][c][y][x] + bias[c] + Up2(prev)[b,c,y,x]
 // (ToRGBF's `+ bias + skip` with the skip's UpsampleO = upfirdn2d(up=2, pad=(2,1)) inline;
 //  models.py:435-447,639-655).  3-channel tensors: negligible traffic.
@@ -503,18 +672,18 @@ __global__ void rgb_combine_kernel(const float* __restrict__ part, int nparts, i
     const int h2 = H / 2, w2 = W / 2;
     const float* src = prev + static_cast<size_t>(bc) * h2 * w2;
     float u = 0.f;
+    // zero-insert upsampling: only taps with (y + ky - 2) even hit a sample, i.e. ky = (y&1) + 2j
+    // (2 x 2 taps of the 4 x 4 kernel), at input row (y + ky)/2 - 1
 #pragma unroll
-    for (int ky = 0; ky < 4; ++ky) {
-      const int uy = y + ky - 2;
-      if (uy < 0 || (uy & 1)) continue;
-      const int iy = uy >> 1;
-      if (iy >= h2) continue;
+    for (int j = 0; j < 2; ++j) {
+      const int ky = (y & 1) + 2 * j;
+      const int iy = ((y + ky) >> 1) - 1;
+      if (iy < 0 || iy >= h2) continue;
 #pragma unroll
-      for (int kx = 0; kx < 4; ++kx) {
-        const int ux = x + kx - 2;
-        if (ux < 0 || (ux & 1)) continue;
-        const int ix = ux >> 1;
-        if (ix >= w2) continue;
+      for (int i = 0; i < 2; ++i) {
+        const int kx = (x & 1) + 2 * i;
+        const int ix = ((x + kx) >> 1) - 1;
+        if (ix < 0 || ix >= w2) continue;
         u = fmaf(__ldg(src + iy * w2 + ix), __ldg(k4 + (3 - ky) * 4 + (3 - kx)), u);
       }
     }
@@ -544,7 +713,7 @@ struct StyleJobs {
 // each of the 8 warps owns one output channel and reads its weight row once.
 __global__ void __launch_bounds__(256)
 styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, float scale,
-              const StyleJobs jobs) {
+              float bias_mul, int act, const StyleJobs jobs) {
   extern __shared__ float xs[];            // [B][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int l = 0;
@@ -560,7 +729,7 @@ styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, floa
   const int C = jobs.chans[l];
   if (c >= C) return;
   const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
-  const float bv = __ldg(jobs.bias[l] + c);
+  const float bv = __ldg(jobs.bias[l] + c) * bias_mul;
   float* out = jobs.out[l];
   for (int b0 = 0; b0 < B; b0 += 8) {
     float acc[8];
@@ -577,9 +746,76 @@ styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, floa
       float a = acc[i];
 #pragma unroll
       for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == 0 && b0 + i < B) out[static_cast<size_t>(b0 + i) * C + c] = a + bv;
+      if (lane == 0 && b0 + i < B) {
+        float v = a + bv;
+        if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;   // fused_leaky_relu
+        out[static_cast<size_t>(b0 + i) * C + c] = v;
+      }
     }
   }
+}
+
+// z * rsqrt(mean(z^2, dim=1) + 1e-8)   (PixelNormL, models.py:609-614); one warp per row
+__global__ void pixel_norm_kernel(const float* __restrict__ z, int B, int K, float* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* src = z + static_cast<size_t>(row) * K;
+  float ss = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float v = __ldg(src + k);
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float r = rsqrtf(ss / static_cast<float>(K) + 1e-8f);
+  for (int k = lane; k < K; k += 32) out[static_cast<size_t>(row) * K + k] = __ldg(src + k) * r;
+}
+
+// ---------------------------------------------------------------------------
+// demod_multi: the demodulation factors of EVERY styled conv of the generator in one launch
+// (they only depend on the styles), plus the ToRGB modulated 1x1 weights
+//   kind 0: out[b,o]   = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)        one warp per (b,o)
+//   kind 1: out[b,c,i] = (wscale * w[c,i]) * style[b,i]   (c < 3; `wsq` holds w) one warp per (b,c)
+// ---------------------------------------------------------------------------
+struct DemodJobs {
+  const float* style[32];
+  const float* wsq[32];
+  float* out[32];
+  int cout[32];
+  int cin[32];
+  int kind[32];
+  float wscale[32];
+  int first_block[33];
+  int n;
+};
+
+__global__ void __launch_bounds__(256)
+demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
+  int l = 0;
+  const int blk = blockIdx.x;
+  while (blk >= jobs.first_block[l + 1]) ++l;
+  const int gw = (blk - jobs.first_block[l]) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int Cout = jobs.cout[l], Cin = jobs.cin[l];
+  if (gw >= B * Cout) return;
+  const int b = gw / Cout, o = gw - b * Cout;
+  const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
+  const float* q = jobs.wsq[l] + static_cast<size_t>(o) * Cin;
+  if (jobs.kind[l] == 1) {
+    const float ws = jobs.wscale[l];
+    float* dst = jobs.out[l] + static_cast<size_t>(gw) * Cin;
+    for (int i = lane; i < Cin; i += 32) dst[i] = (ws * __ldg(q + i)) * __ldg(s + i);
+    return;
+  }
+  float acc = 0.f;
+  for (int i = lane; i < Cin; i += 32) {
+    const float sv = __ldg(s + i);
+    acc = fmaf(sv * sv, __ldg(q + i), acc);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) jobs.out[l][gw] = rsqrtf(acc + eps);
 }
 
 inline int grid_for(long long n, int threads, int cap = 148 * 16) {
@@ -719,7 +955,32 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
     set_last_error("blur_up_fused: grid.z %lld too large", gz);
     return RW_ERR_BAD_ARG;
   }
-  dim3 grid((Wo + 1 + BF_TX - 1) / BF_TX, (Ho + 1 + BF_TY - 1) / BF_TY, static_cast<unsigned>(gz));
+  const int tiles_x = (Wo + 1 + BF_TX - 1) / BF_TX, tiles_y = (Ho + 1 + BF_TY - 1) / BF_TY;
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char* e = getenv("RW_BLUR_PIPE");
+    use_pipe = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_pipe) {
+    static bool attr2 = false;
+    if (!attr2) {
+      int rc = check_cuda(cudaFuncSetAttribute(blur_up_pipe_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(2 * smem)),
+                          "blur_up_pipe smem attr");
+      if (rc) return rc;
+      attr2 = true;
+    }
+    const long long ntiles = static_cast<long long>(tiles_x) * tiles_y * gz;
+    long long g = 2LL * device_sm_count();
+    if (g > ntiles) g = ntiles;
+    blur_up_pipe_kernel<<<static_cast<unsigned>(g), 256, 2 * smem, stream>>>(
+        t_cl, B, C, Hin, Win, k4, noise, noise_bstride, noise_w, bias, act, next_scale,
+        static_cast<__nv_bfloat16*>(next_hi), static_cast<__nv_bfloat16*>(next_lo), y_out, tiles_x,
+        tiles_y, ntiles);
+    return check_cuda(cudaGetLastError(), "blur_up_pipe launch");
+  }
+  dim3 grid(tiles_x, tiles_y, static_cast<unsigned>(gz));
   blur_up_fused_kernel<<<grid, 256, smem, stream>>>(
       t_cl, B, C, Hin, Win, k4, noise, noise_bstride, noise_w, bias, act, next_scale,
       static_cast<__nv_bfloat16*>(next_hi), static_cast<__nv_bfloat16*>(next_lo), y_out);
@@ -734,9 +995,9 @@ int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const
   return check_cuda(cudaGetLastError(), "rgb_combine launch");
 }
 
-int styles_launch(const float* latent, int B, int n_latent, int K, float scale, int n,
-                  const float* const* w, const float* const* bias, float* const* out,
-                  const int* lat, const int* chans, cudaStream_t stream) {
+int styles_launch(const float* latent, int B, int n_latent, int K, float scale, float bias_mul,
+                  int act, int n, const float* const* w, const float* const* bias,
+                  float* const* out, const int* lat, const int* chans, cudaStream_t stream) {
   if (n < 1 || n > 32) {
     set_last_error("styles: %d layers (max 32)", n);
     return RW_ERR_BAD_ARG;
@@ -767,8 +1028,41 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     if (rc) return rc;
     attr = smem;
   }
-  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, jobs);
+  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, bias_mul, act, jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
+}
+
+int pixel_norm_launch(const float* z, int B, int K, float* out, cudaStream_t stream) {
+  const int blocks = (B * 32 + 255) / 256;
+  pixel_norm_kernel<<<blocks, 256, 0, stream>>>(z, B, K, out);
+  return check_cuda(cudaGetLastError(), "pixel_norm launch");
+}
+
+int demod_multi_launch(int B, float eps, int n, const float* const* style,
+                       const float* const* wsq, float* const* out, const int* cout,
+                       const int* cin, const int* kind, const float* wscale,
+                       cudaStream_t stream) {
+  if (n < 1 || n > 32) {
+    set_last_error("demod_multi: %d jobs (max 32)", n);
+    return RW_ERR_BAD_ARG;
+  }
+  DemodJobs jobs;
+  jobs.n = n;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    jobs.style[i] = style[i];
+    jobs.wsq[i] = wsq[i];
+    jobs.out[i] = out[i];
+    jobs.cout[i] = cout[i];
+    jobs.cin[i] = cin[i];
+    jobs.kind[i] = kind[i];
+    jobs.wscale[i] = wscale[i];
+    jobs.first_block[i] = blocks;
+    blocks += (B * cout[i] + 7) / 8;
+  }
+  jobs.first_block[n] = blocks;
+  demod_multi_kernel<<<blocks, 256, 0, stream>>>(B, eps, jobs);
+  return check_cuda(cudaGetLastError(), "demod_multi launch");
 }
 
 int prep_phase_keys_launch(const float* g, const float* scale_bc, int B, int C, int H, int W,

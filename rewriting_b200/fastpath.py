@@ -83,6 +83,33 @@ def eligible(model, z):
     return _layer_list(model) is not None
 
 
+def _mapping(model, z, stream):
+    """w = AdjustLatent(style MLP(z)) as [B, style_dim] (models.py:487-533,570-583,609-614):
+    PixelNorm + one fused EqualLinear(lrelu) launch per layer instead of sgemm + bias_act + two
+    elementwise kernels each.  All n_latent copies of the reference's `latent` are this row."""
+    from .utils.stylegan2 import models as sg2
+    mods = list(model.style._modules.values())
+    pristine = (len(mods) > 1 and isinstance(mods[0], sg2.PixelNormL) and
+                all(type(m) is sg2.EqualLinearL and m.activation and m.bias is not None
+                    for m in mods[1:]))
+    if not pristine:
+        return model.latents(model.style(model.bag_in(z))).latent[:, 0].contiguous()
+    z = z.contiguous()
+    B, K = z.shape
+    x = torch.empty_like(z)
+    _cabi.call('rw_pixel_norm', _p(z), B, K, _p(x), stream)
+    for m in mods[1:]:
+        cout, kin = m.weight.shape
+        out = torch.empty((B, cout), dtype=torch.float32, device=z.device)
+        _cabi.call('rw_equal_linear', _p(x), B, kin, _p(m.weight), _p(m.bias), cout,
+                   float(m.scale), float(m.lr_mul), 1, _p(out), stream)
+        x = out
+    lat = model.latents
+    if lat.truncation != 1.0 and lat.latent_avg.ndim > 0:      # AdjustLatent.forward
+        x = lat.latent_avg + lat.truncation * (x - lat.latent_avg)
+    return x
+
+
 def forward(model, z, upto_key_layer=None):
     """image [B,3,size,size] (or KeyPlanes of `layer<upto_key_layer>`'s key)."""
     from .utils.stylegan2 import models as sg2
@@ -90,10 +117,15 @@ def forward(model, z, upto_key_layer=None):
     if layers is None:
         raise _cabi.RwError('fastpath: the module tree is not a pristine SeqStyleGAN2')
     dev = z.device
-    d = model.latents(model.style(model.bag_in(z)))
-    latent = d.latent                                    # [B, n_latent, 512]
     B = z.shape[0]
     stream = _stream()
+    w_lat = _mapping(model, z, stream)                   # [B, 512]: every latent slot is this row
+    K = w_lat.shape[1]
+    run = [l for l in layers if upto_key_layer is None or l[0] < upto_key_layer]
+    if upto_key_layer is not None:
+        # key collection: the running RGB image feeds nothing, skip every ToRGB
+        layers = [(num, sconv, lat, None, None) for num, sconv, lat, _, _ in layers]
+        run = [(num, sconv, lat, None, None) for num, sconv, lat, _, _ in run]
 
     # all styles up front (they only depend on the latent): ONE launch for the 13 + 7
     # modulation linears instead of 20 tiny sgemms
@@ -102,20 +134,39 @@ def forward(model, z, upto_key_layer=None):
         mods.append((('conv', num), sconv.mconv.modulation, lat))
         if rgb is not None:
             mods.append((('rgb', num), rgb.conv.modulation, rgb_lat))
-    latent = latent.contiguous()
     n = len(mods)
     outs = [torch.empty((B, m.weight.shape[0]), dtype=torch.float32, device=dev) for _, m, _ in mods]
     PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
-    _cabi.call('rw_styles', _p(latent), B, latent.shape[1], latent.shape[2],
-               float(mods[0][1].scale), n,
+    _cabi.call('rw_styles', _p(w_lat), B, 1, K, float(mods[0][1].scale), n,
                PtrArr(*[m.weight.data_ptr() for _, m, _ in mods]),
                PtrArr(*[m.bias.data_ptr() for _, m, _ in mods]),
                PtrArr(*[o.data_ptr() for o in outs]),
-               IntArr(*[li for _, _, li in mods]),
+               IntArr(*([0] * n)),
                IntArr(*[m.weight.shape[0] for _, m, _ in mods]), stream)
     styles, rgb_styles = {}, {}
     for (kind, num), o in zip([k for k, _, _ in mods], outs):
         (styles if kind == 'conv' else rgb_styles)[num] = o
+
+    # ... and everything else that only depends on the styles: the demodulation factors of every
+    # conv and ToRGB's modulated 1x1 weights, one launch
+    demods, rgb_ws, jobs = {}, {}, []
+    for num, sconv, lat, rgb, rgb_lat in run:
+        dconv = sconv.mconv.dconv
+        wsq = ops.weight_planes(dconv.weight, 'fwd')[2]
+        demods[num] = torch.empty((B, dconv.out_channel), dtype=torch.float32, device=dev)
+        jobs.append((styles[num], wsq, demods[num], dconv.out_channel, dconv.in_channel, 0, 1.0))
+        if rgb is not None:
+            C = dconv.out_channel
+            rgb_ws[num] = torch.empty((B, 3, C), dtype=torch.float32, device=dev)
+            jobs.append((rgb_styles[num], rgb.conv.weight.detach().reshape(3, C), rgb_ws[num], 3, C,
+                         1, 1.0 / math.sqrt(C)))
+    if jobs:
+        nj = len(jobs)
+        P, I, Fl = ctypes.c_void_p * nj, ctypes.c_int * nj, ctypes.c_float * nj
+        _cabi.call('rw_demod_multi', B, 1e-8, nj, P(*[j[0].data_ptr() for j in jobs]),
+                   P(*[j[1].data_ptr() for j in jobs]), P(*[j[2].data_ptr() for j in jobs]),
+                   I(*[j[3] for j in jobs]), I(*[j[4] for j in jobs]), I(*[j[5] for j in jobs]),
+                   Fl(*[j[6] for j in jobs]), stream)
 
     x0 = model.input.input
     H = W = x0.shape[2]
@@ -130,8 +181,8 @@ def forward(model, z, upto_key_layer=None):
         mc = sconv.mconv
         dconv = mc.dconv
         Cin, Cout = dconv.in_channel, dconv.out_channel
-        w_hi, w_lo, wsq = ops.weight_planes(dconv.weight, 'fwd')
-        dm = ops.demod_factors(styles[num], wsq)
+        w_hi, w_lo, _ = ops.weight_planes(dconv.weight, 'fwd')
+        dm = demods[num]
         nxt = layers[idx + 1] if idx + 1 < len(layers) else None
         next_scale = styles[nxt[0]] if nxt is not None else None
         nw = sconv.noise.weight.detach()
@@ -161,9 +212,7 @@ def forward(model, z, upto_key_layer=None):
             rgb_w = rgb_part = None
             ntile = Cout // 64          # one ToRGB partial per 64-channel epilogue group
             if rgb is not None:
-                s_rgb = rgb_styles[num]                                          # [B, Cout]
-                w3 = rgb.conv.weight.detach().reshape(3, Cout) * (1.0 / math.sqrt(Cout))
-                rgb_w = (w3[None, :, :] * s_rgb[:, None, :]).contiguous()       # [B,3,Cout]
+                rgb_w = rgb_ws[num]                                              # [B,3,Cout]
                 rgb_part = torch.empty((ntile, B, 3, H, W), dtype=torch.float32, device=dev)
             _cabi.call('rw_modconv_fwd_fused', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
                        _p(dm), _p(noise), noise.stride(0), _p(nw), _p(bias), 1, B, Cin, Cout, H, W,

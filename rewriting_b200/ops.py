@@ -337,92 +337,91 @@ class StyledConvFunction(torch.autograd.Function):
         ctx.cfg = (upsample, demodulate, with_noise, with_act, pre_modulated)
         ctx.blur_kernel = blur_kernel
         ctx.wholder = wholder
-        needs_bwd = any(ctx.needs_input_grad)
-        ctx.planes = planes if needs_bwd else None
-        ctx.t_up = t_up if needs_bwd else None      # conv_transpose output * demod (up layers)
+        ctx.planes = planes if any(ctx.needs_input_grad) else None
         return y
 
     @staticmethod
     def backward(ctx, gy):
+        """Five HBM passes + two tensor-core GEMMs (csrc/bwd.cu):
+        act_grad_reduce (gy, y -> g_pre and every per-(b,o) reduction) -> gradient planes
+        (prep_keys, or blur^T + phase split for up layers) -> dgrad row-GEMM -> dgrad_finish
+        (gx, dstyle) ; wgrad col-GEMM -> wgrad_finish (demodulation term, Parameter layout)."""
         x, style, weight, noise_weight, bias, y, dm = ctx.saved_tensors
         upsample, demodulate, with_noise, with_act, pre_modulated = ctx.cfg
         if ctx.planes is None:
             raise _cabi.RwError('StyledConvFunction.backward: forward ran without autograd state')
+        need_x, need_style, need_w = ctx.needs_input_grad[:3]
         gy = _f32c(gy)
         B, Cin, H, W = x.shape
         Cout = weight.shape[-4]
         sc = 1.0 / math.sqrt(Cin * 9)
-        w4 = weight.detach().reshape(Cout, Cin, 3, 3)
         Ho, Wo = (2 * H, 2 * W) if upsample else (H, W)
-        # through the activation: gate on the sign of the saved output
-        if with_act:
-            g_pre = fused_bias_act_raw(gy, None, y, 3, 1, LRELU_SLOPE, LRELU_GAIN)
-        else:
+        dev = x.device
+        has_noise = with_noise and noise_weight is not None
+        has_bias = with_act and bias is not None
+        noise = noise_table(B, Ho * Wo, dev) if has_noise else None
+        nw = _f32c(noise_weight.detach()) if has_noise else None
+        bv = _f32c(bias.detach()) if has_bias else None
+        # one pass over (gy, y): gradient through the activation (gate on the sign of the saved
+        # output) and the three per-(b,o) pixel reductions
+        red = torch.empty((3, B, Cout), dtype=torch.float32, device=dev)
+        g_pre = torch.empty_like(gy) if with_act else None
+        _cabi.call('rw_act_grad_reduce', _p(gy), _p(y), _p(noise),
+                   noise.stride(0) if has_noise else 0, _p(nw), _p(bv), 1 if with_act else 0,
+                   B, Cout, Ho * Wo, _p(g_pre), _p(red[0]), _p(red[1]), _p(red[2]), _stream())
+        if g_pre is None:
             g_pre = gy
-        g_bias = g_pre.sum(dim=(0, 2, 3)) if (with_act and bias is not None) else None
-        g_nw = None
-        noise = noise_table(B, Ho * Wo, x.device) if with_noise else None
-        if with_noise and noise_weight is not None:
-            g_nw = (g_pre.sum(dim=1).reshape(B, -1) * noise).sum().reshape(1)
+        g_bias = red[0].sum(dim=0) if has_bias else None
+        g_nw = red[2].sum().reshape(noise_weight.shape) if has_noise else None
+        s_dot = red[1] if demodulate else None        # = dL/d(demod) * demod
         k_planes = ctx.planes
+        need_dk = need_x or (need_style and not pre_modulated)
+        dk = dwt = None
         if upsample:
-            # adjoint of the blur (upfirdn2d with the flipped kernel and the adjoint padding)
-            kflip = torch.flip(ctx.blur_kernel, [0, 1]).contiguous()
-            g_t = upfirdn2d_raw(g_pre.reshape(B * Cout, Ho, Wo, 1), kflip, 1, 1, 1, 1, 2, 2, 2, 2)
-            g_t = g_t.view(B, Cout, 2 * H + 1, 2 * W + 1)
             rows = B * (H + 1) * (W + 1)
-            gph_hi = torch.empty((rows, 4 * Cout), dtype=torch.bfloat16, device=x.device)
+            gph_hi = torch.empty((rows, 4 * Cout), dtype=torch.bfloat16, device=dev)
             gph_lo = torch.empty_like(gph_hi)
-            _cabi.call('rw_prep_phase_keys', _p(g_t), _p(dm), B, Cout, H, W, _p(gph_hi),
-                       _p(gph_lo), _stream())
-            wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad_up')
-            dk = torch.empty((B, Cin, H, W), dtype=torch.float32, device=x.device)
-            _cabi.call('rw_modconv_up_dgrad', _p(gph_hi), _p(gph_lo), _p(wd_hi), _p(wd_lo), None,
-                       B, Cin, Cout, H, W, _p(dk), _stream())
-            lib = _cabi.load()
-            ws = _workspace(lib.rw_gram_workspace_bytes(Cout, Cin, rows, 9), x.device)
-            dwt = torch.empty((Cout, 9, Cin), dtype=torch.float32, device=x.device)
-            _cabi.call('rw_conv_up_wgrad', _p(gph_hi), _p(gph_lo), _p(k_planes.hi),
-                       _p(k_planes.lo), rows, Cout, Cin, W + 1, _p(dwt), _p(ws), ws.numel() * 4,
-                       _stream())
-            Gd = (g_t * ctx.t_up).sum(dim=(2, 3)) if demodulate else None   # = dL/d(demod) * demod
+            # blur^T(g_pre) * demod, split into the 4 conv_transpose phases
+            _cabi.call('rw_blur_adj_phase_keys', _p(g_pre), _p(dm), _p(_f32c(ctx.blur_kernel)), B,
+                       Cout, H, W, _p(gph_hi), _p(gph_lo), _stream())
+            if need_dk:
+                wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad_up')
+                dk = torch.empty((B, Cin, H, W), dtype=torch.float32, device=dev)
+                _cabi.call('rw_modconv_up_dgrad', _p(gph_hi), _p(gph_lo), _p(wd_hi), _p(wd_lo),
+                           None, B, Cin, Cout, H, W, _p(dk), _stream())
+            if need_w:
+                lib = _cabi.load()
+                ws = _workspace(lib.rw_gram_workspace_bytes(Cout, Cin, rows, 9), dev)
+                dwt = torch.empty((Cout, 9, Cin), dtype=torch.float32, device=dev)
+                _cabi.call('rw_conv_up_wgrad', _p(gph_hi), _p(gph_lo), _p(k_planes.hi),
+                           _p(k_planes.lo), rows, Cout, Cin, W + 1, _p(dwt), _p(ws),
+                           ws.numel() * 4, _stream())
         else:
-            # gradient planes of g_t = g_pre * demod
-            g_planes, _ = prep_keys(g_pre, dm)
-            # dgrad: dk = conv(g_t, flip(W)^T)
-            wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad')
-            dk = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)
-            dwt = conv_wgrad_planes(g_planes, k_planes)            # [Cout, 9, Cin]
-            Gd = None
-            if demodulate:
-                # recover t*demod = pre-activation - noise - bias from the saved output
-                if with_act:
-                    pre = torch.where(y > 0, y / LRELU_GAIN, y / (LRELU_SLOPE * LRELU_GAIN))
-                    if bias is not None:
-                        pre = pre - bias.detach().view(1, -1, 1, 1)
-                else:
-                    pre = y
-                if with_noise and noise_weight is not None:
-                    pre = pre - noise_weight.detach() * noise.view(B, 1, H, W)
-                Gd = (g_pre * pre).sum(dim=(2, 3))
-        if pre_modulated:
-            gx, g_style = dk, None
-        else:
-            gx = dk * style[:, :, None, None]
-            g_style = (dk * x).sum(dim=(2, 3))
-        gW = (sc * dwt).permute(0, 2, 1).reshape(Cout, Cin, 3, 3)
-        if demodulate:
-            coef = Gd * dm * dm
-            s2 = style * style
-            # d demod/dW = -demod^3 * sc^2 * W * s^2 ;  dL/ddemod = Gd/demod
-            gW = gW - (sc * sc) * w4 * torch.matmul(coef.t(), s2)[:, :, None, None]
-            if g_style is not None:
-                wsq = ctx.wholder.planes('fwd')[2]
-                g_style = g_style - style * torch.matmul(coef, wsq)
-            elif pre_modulated and style.requires_grad:
-                wsq = ctx.wholder.planes('fwd')[2]
-                g_style = -style * torch.matmul(coef, wsq)
-        gW = gW.reshape(weight.shape)
+            g_planes, _ = prep_keys(g_pre, dm)          # planes of g_t = g_pre * demod
+            if need_dk:
+                wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad')
+                dk = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)   # conv(g_t, flip(W)^T)
+            if need_w:
+                dwt = conv_wgrad_planes(g_planes, k_planes)        # [Cout, 9, Cin]
+        gx = g_style = gs_raw = None
+        if need_dk:
+            if pre_modulated:
+                gx = dk
+            else:
+                gs_raw = torch.empty((B, Cin), dtype=torch.float32, device=dev)
+                _cabi.call('rw_dgrad_finish', _p(dk), _p(x), _p(style), B, Cin, H * W, _p(gs_raw),
+                           _stream())
+                gx = dk                                  # scaled by style in place
+        if need_style and (gs_raw is not None or demodulate):
+            wsq = ctx.wholder.planes('fwd')[2] if demodulate else None
+            g_style = torch.empty((B, Cin), dtype=torch.float32, device=dev)
+            _cabi.call('rw_style_grad_finish', _p(gs_raw), _p(style), _p(s_dot), _p(dm), _p(wsq),
+                       B, Cout, Cin, _p(g_style), _stream())
+        gW = None
+        if need_w:
+            gW = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+            _cabi.call('rw_wgrad_finish', _p(dwt), _p(_f32c(weight.detach())), _p(s_dot), _p(dm),
+                       _p(style), B, Cout, Cin, sc, _p(gW), _stream())
         return gx, g_style, gW, g_nw, g_bias, None, None, None, None, None, None, None
 
 
