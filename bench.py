@@ -390,6 +390,22 @@ def main():
             extra['insert_loop'] = bench_insert(model, z_dev, device)
         except Exception as e:  # noqa: BLE001
             extra['insert_loop'] = {'error': '%s: %s' % (type(e).__name__, e)}
+        if world == 1:
+            # BASELINE.json configs[1]: fused StyledConv forward + backward (dX, dstyle, dW, dbias,
+            # dnoise), every layer shape of the 256^2 generator at batch 32
+            try:
+                del key_runner
+                torch.cuda.empty_cache()
+                from tools import bench_modconv
+                r = bench_modconv.main(B=BATCH, quiet=True, save=False)
+                sm = r['summary']
+                extra['modconv_fwdbwd_b32'] = {
+                    'fwd_ms': sm['total_fwd_ms'], 'fwdbwd_ms': sm['total_fwdbwd_ms'],
+                    'fwd_TFLOPs': sm['fwd_TFLOPs'], 'fwdbwd_TFLOPs': sm['fwdbwd_TFLOPs'],
+                    'per_layer_fwdbwd_ms': {l['layer']: round(l['fwdbwd_ms'], 4) for l in r['layers']},
+                    'note': sm['note']}
+            except Exception as e:  # noqa: BLE001
+                extra['modconv_fwdbwd_b32'] = {'error': '%s: %s' % (type(e).__name__, e)}
 
     if rank == 0:
         peaks = measured_peaks()

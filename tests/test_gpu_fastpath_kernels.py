@@ -1,0 +1,134 @@
+"""GPU (B200): the small kernels of the generation fast path against plain torch fp32
+(mapping network layers, batched demodulation / ToRGB weights, ToRGB combine, pipelined blur)."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+from oracle import sg2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pixel_norm_and_equal_linear_vs_torch():
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(0)
+    for B in (1, 5, 32, 40):
+        z = torch.randn(B, 512, device='cuda')
+        out = torch.empty_like(z)
+        _cabi.call('rw_pixel_norm', ops._p(z), B, 512, ops._p(out), ops._stream())
+        want = z * torch.rsqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)
+        assert torch.allclose(out, want, rtol=1e-5, atol=1e-6)
+        w = torch.randn(512, 512, device='cuda') / 0.01
+        b = torch.randn(512, device='cuda')
+        lr_mul = 0.01
+        scale = (1 / math.sqrt(512)) * lr_mul
+        for act in (1, 0):
+            y = torch.empty(B, 512, device='cuda')
+            _cabi.call('rw_equal_linear', ops._p(out), B, 512, ops._p(w), ops._p(b), 512, scale,
+                       lr_mul, act, ops._p(y), ops._stream())
+            ref = torch.nn.functional.linear(want.double(), (w * scale).double()) + (b * lr_mul).double()
+            if act:
+                ref = torch.nn.functional.leaky_relu(ref, 0.2) * math.sqrt(2)
+            assert (y.double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_mapping_network_equals_module_path(seeded_model):
+    import copy
+    from rewriting_b200 import fastpath, ops
+    model = copy.deepcopy(seeded_model).cuda().eval()
+    z = torch.randn(7, 512, device='cuda')
+    with torch.no_grad():
+        got = fastpath._mapping(model, z, ops._stream())
+        want = model.latents(model.style(model.bag_in(z))).latent
+    assert want.shape == (7, model.n_latent, 512)
+    assert (want - want[:, :1]).abs().max().item() == 0          # all latent slots identical
+    assert (got - want[:, 0]).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
+    ref = orc.mapping({k: v.cpu() for k, v in model.state_dict().items()}, z.cpu())
+    assert (got.cpu() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_demod_multi_vs_torch():
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(1)
+    B = 3
+    shapes = [(512, 512), (256, 512), (128, 256)]           # (Cout, Cin)
+    jobs, wants = [], []
+    for cout, cin in shapes:
+        style = torch.randn(B, cin, device='cuda')
+        wsq = torch.rand(cout, cin, device='cuda')
+        out = torch.empty(B, cout, device='cuda')
+        jobs.append((style, wsq, out, cout, cin, 0, 1.0))
+        wants.append(torch.rsqrt((style.double() ** 2) @ wsq.double().t() + 1e-8))
+        w3 = torch.randn(3, cin, device='cuda')
+        out3 = torch.empty(B, 3, cin, device='cuda')
+        ws = 1.0 / math.sqrt(cin)
+        jobs.append((style, w3, out3, 3, cin, 1, ws))
+        wants.append(((w3 * ws)[None] * style[:, None, :]).double())
+    n = len(jobs)
+    P, I, Fl = ctypes.c_void_p * n, ctypes.c_int * n, ctypes.c_float * n
+    _cabi.call('rw_demod_multi', B, 1e-8, n, P(*[j[0].data_ptr() for j in jobs]),
+               P(*[j[1].data_ptr() for j in jobs]), P(*[j[2].data_ptr() for j in jobs]),
+               I(*[j[3] for j in jobs]), I(*[j[4] for j in jobs]), I(*[j[5] for j in jobs]),
+               Fl(*[j[6] for j in jobs]), ops._stream())
+    for j, want in zip(jobs, wants):
+        assert (j[2].double() - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize('B,H,W,nparts,has_prev', [(2, 8, 8, 4, True), (1, 4, 4, 8, False),
+                                                   (3, 16, 12, 2, True)])
+def test_rgb_combine_vs_oracle_upsample(B, H, W, nparts, has_prev):
+    """sum of ToRGB partials + bias + UpsampleO(prev) (models.py:435-447,639-655)"""
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(2)
+    part = torch.randn(nparts, B, 3, H, W, device='cuda')
+    bias = torch.randn(3, device='cuda')
+    prev = torch.randn(B, 3, H // 2, W // 2, device='cuda') if has_prev else None
+    k4 = (orc.make_kernel([1, 3, 3, 1]) * 4 + 0.03 * torch.randn(4, 4)).cuda()
+    out = torch.empty(B, 3, H, W, device='cuda')
+    _cabi.call('rw_rgb_combine', ops._p(part), nparts, B, H, W, ops._p(bias), ops._p(prev),
+               ops._p(k4) if has_prev else None, ops._p(out), ops._stream())
+    want = part.sum(0) + bias.view(1, 3, 1, 1)
+    if has_prev:
+        want = want + orc.upfirdn2d(prev.cpu(), k4.cpu(), up=2, pad=(2, 1)).cuda()
+    assert (out - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize('B,C,H,W', [(2, 64, 4, 4), (1, 128, 5, 7), (3, 64, 16, 16), (2, 128, 33, 9)])
+def test_blur_up_fused_vs_layer_kernels(B, C, H, W):
+    """pipelined persistent blur (channels-last phases in, next-layer planes + NCHW out) ==
+    blur_up_act on the NCHW conv_transpose output -> prep_keys"""
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(3)
+    dev = 'cuda'
+    Ht, Wt, Ho, Wo = 2 * H + 1, 2 * W + 1, 2 * H, 2 * W
+    t = torch.randn(B, C, Ht, Wt, device=dev)
+    kern = (orc.make_kernel([1, 3, 3, 1]) * 4 + 0.03 * torch.randn(4, 4)).to(dev)
+    noise = ops.noise_table(B, Ho * Wo, dev)
+    nw = torch.tensor([0.37], device=dev)
+    bias = torch.randn(C, device=dev)
+    nscale = torch.randn(B, C, device=dev)
+    # channels-last phase tensor [4][rows][C] (conv_tc out_mode 1): zero outside the valid extent
+    rows = B * (H + 1) * (W + 1)
+    t_cl = torch.zeros(4, B, H + 1, W + 1, C, device=dev)
+    for a in range(2):
+        for b in range(2):
+            sub = t[:, :, a::2, b::2]                      # [B,C,(H+1 or H),(W+1 or W)]
+            t_cl[a * 2 + b, :, :sub.shape[2], :sub.shape[3]] = sub.permute(0, 2, 3, 1)
+    t_cl = t_cl.reshape(4, rows, C).contiguous()
+    rows_o = B * (Ho + 1) * (Wo + 1)
+    nh = torch.empty(rows_o, C, dtype=torch.bfloat16, device=dev)
+    nl = torch.empty_like(nh)
+    y = torch.empty(B, C, Ho, Wo, device=dev)
+    _cabi.call('rw_blur_up_fused', ops._p(t_cl), B, C, H, W, ops._p(kern), ops._p(noise),
+               noise.stride(0), ops._p(nw), ops._p(bias), 1, ops._p(nscale), ops._p(nh),
+               ops._p(nl), ops._p(y), ops._stream())
+    want = ops.blur_up_act(t, kern, noise, nw, bias, True)
+    assert (y - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
+    planes, _ = ops.prep_keys(want, nscale)
+    got = nh.float() + nl.float()
+    ref = planes.hi.float() + planes.lo.float()
+    assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    v = got.view(B, Ho + 1, Wo + 1, C)
+    assert v[:, Ho].abs().max() == 0 and v[:, :, Wo].abs().max() == 0       # pad row / column

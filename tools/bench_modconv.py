@@ -26,7 +26,7 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def main(B=32, only=None):
+def main(B=32, only=None, quiet=False, save=True):
     torch.manual_seed(0)
     kern = (torch.tensor([1., 3., 3., 1.])[:, None] * torch.tensor([1., 3., 3., 1.])[None, :])
     kern = (kern / kern.sum() * 4).cuda()
@@ -59,16 +59,21 @@ def main(B=32, only=None):
                    fwd_TFLOPs=flops / tf / 1e9, fwdbwd_TFLOPs=3 * flops / tfb / 1e9)
         out.append(rec)
         tot_f += tf; tot_fb += tfb; fl_f += flops
-        print(json.dumps(rec), flush=True)
+        if not quiet:
+            print(json.dumps(rec), flush=True)
         del x, style, w, gy
         torch.cuda.empty_cache()
     summary = dict(batch=B, total_fwd_ms=tot_f, total_fwdbwd_ms=tot_fb,
                    fwd_TFLOPs=fl_f / tot_f / 1e9, fwdbwd_TFLOPs=3 * fl_f / tot_fb / 1e9,
                    note='layer-level op (fp32 NCHW in/out, prep + conv_tc + epilogue kernels), '
                         'algorithmic FLOPs (1x); operands 3-term split bf16')
-    print(json.dumps(summary))
-    os.makedirs('gpurun_out', exist_ok=True)
-    json.dump(dict(layers=out, summary=summary), open('gpurun_out/modconv_fwdbwd.json', 'w'), indent=1)
+    if not quiet:
+        print(json.dumps(summary))
+    if save:
+        os.makedirs('gpurun_out', exist_ok=True)
+        json.dump(dict(layers=out, summary=summary), open('gpurun_out/modconv_fwdbwd.json', 'w'),
+                  indent=1)
+    return dict(layers=out, summary=summary)
 
 
 if __name__ == '__main__':
