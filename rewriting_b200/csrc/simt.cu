@@ -485,17 +485,27 @@ blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
 }
 
 // ---------------------------------------------------------------------------
-// blur_up_pipe: the same arithmetic as blur_up_fused, restructured for memory-level parallelism.
-// The one-tile-per-CTA kernel above serialises  load -> sync -> FIR -> store  inside a CTA, and
-// at 4 CTAs/SM too few loads are in flight for HBM (measured 2.6 TB/s).  Here CTAs are
-// persistent (2 per SM), walk the tile list with a static stride and prefetch tile i+1 with
-// cp.async (16 B, L2 only, zero-fill outside the image) into the second shared-memory buffer
-// while tile i is filtered: 53.5 KB per CTA are always in flight.
+// blur_up_pipe: blur_up_fused for the generation fast path's configuration (noise + bias +
+// leaky-ReLU, output = the next layer's key planes only), rebuilt after an ncu capture of the
+// one-tile-per-CTA kernel on layer 13 (profiles/: 0.84 ms, DRAM 31 %, issue slots 58 % busy, ALU
+// the top pipe — 607 M warp instructions, of which the 16-tap FIR was only a third):
+//  * persistent CTAs (2 per SM) walk the tile list with a static stride; tile i+1 is prefetched
+//    with cp.async (16 B, zero-fill outside the image) into the second buffer while tile i is
+//    filtered;
+//  * index arithmetic hoisted: the (ly, lx) of a thread's 14 staging slots come from a small
+//    shared table, the tile coordinate advances as a mixed-radix counter (no division in the
+//    loop), channel-block fastest so that both 256-byte halves of a row move together;
+//  * no per-pixel null-pointer branches (the generic kernel keeps those), leaky-ReLU as
+//    max(v, 0.2 v);
+//  * a rank-one 4x4 FIR (the model's [1,3,3,1] x [1,3,3,1]) is applied separably: 176 + 128
+//    instead of 512 FMAs per thread.  Detected on the device (exact rank-one test), other
+//    kernels take the 16-tap loop.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-  const uint32_t nbytes = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nbytes)
-               : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(dst), "f"(0.f) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -503,151 +513,232 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-struct BlurTile {
-  int b, c0, ox0, oy0;
+constexpr int BF_NPOS = BF_PH * BF_PW;                 // 209 staged positions per tile
+static_assert((BF_TY & 1) == 0 && (BF_TX & 1) == 0 && BF_TX == 16 && BF_PW == 19,
+              "the staging code below relies on odd tile origins and a 16 + 3 column split");
+
+// mixed-radix tile coordinate: digit 0 = channel block, 1 = tile x, 2 = tile y, 3 = sample
+struct BlurCoord {
+  int d[4];
 };
 
-__device__ __forceinline__ BlurTile blur_tile(long long t, int tiles_x, int tiles_y, int cblocks) {
-  BlurTile r;
-  const int bx = static_cast<int>(t % tiles_x);
-  const long long q = t / tiles_x;
-  const int by = static_cast<int>(q % tiles_y);
-  const int bz = static_cast<int>(q / tiles_y);
-  r.b = bz / cblocks;
-  r.c0 = (bz - r.b * cblocks) * BF_C;
-  r.ox0 = bx * BF_TX;
-  r.oy0 = by * BF_TY;
-  return r;
+__device__ __forceinline__ BlurCoord blur_coord(unsigned t, const int (&radix)[4]) {
+  BlurCoord c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    c.d[i] = static_cast<int>(t % static_cast<unsigned>(radix[i]));
+    t /= static_cast<unsigned>(radix[i]);
+  }
+  c.d[3] = static_cast<int>(t);
+  return c;
+}
+
+__device__ __forceinline__ void blur_coord_add(BlurCoord& c, const BlurCoord& step,
+                                               const int (&radix)[4]) {
+  int carry = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int v = c.d[i] + step.d[i] + carry;
+    carry = v >= radix[i] ? 1 : 0;
+    c.d[i] = v - (carry ? radix[i] : 0);
+  }
+  c.d[3] += step.d[3] + carry;
 }
 
 __global__ void __launch_bounds__(256, 2)
 blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
                     const float* __restrict__ k4, const float* __restrict__ noise,
                     long long noise_bstride, const float* __restrict__ noise_w,
-                    const float* __restrict__ bias, int act,
-                    const float* __restrict__ next_scale, __nv_bfloat16* __restrict__ next_hi,
-                    __nv_bfloat16* __restrict__ next_lo, float* __restrict__ y_out,
-                    int tiles_x, int tiles_y, long long ntiles) {
-  extern __shared__ float4 tile4[];      // 2 x [BF_PH*BF_PW][16 quads]
+                    const float* __restrict__ bias, const float* __restrict__ next_scale,
+                    __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo,
+                    int tiles_x, int tiles_y, unsigned ntiles) {
+  extern __shared__ float4 tile4[];      // 2 x [BF_NPOS][16 quads]
   __shared__ float kf[16];
-  constexpr int TILE_ELEMS = BF_PH * BF_PW * 16;
+  __shared__ int sep_flag;
+  constexpr int TILE_ELEMS = BF_NPOS * 16;
   const int Ho = 2 * H, Wo = 2 * W;
   const int Hp_in = H + 1, Wp_in = W + 1;
-  const long long rows_in = static_cast<long long>(B) * Hp_in * Wp_in;
-  const int cblocks = C / BF_C;
+  const int rows_in = B * Hp_in * Wp_in;                 // 4 * rows_in < 2^31 (checked on the host)
+  const int radix[4] = {C / BF_C, tiles_x, tiles_y, B};
   const int tid = threadIdx.x;
   if (tid < 16) kf[tid] = __ldg(k4 + 15 - tid);   // flipped kernel (upfirdn2d correlates)
+  if (tid == 0) {
+    // rank one  <=>  k[i][j] * k[0][0] == k[i][0] * k[0][j]  (exact for [1,3,3,1] (x) [1,3,3,1])
+    bool sep = __ldg(k4 + 15) != 0.f;
+    for (int a = 0; a < 4; ++a)
+      for (int bb = 0; bb < 4; ++bb)
+        sep = sep && (__ldg(k4 + 15 - (a * 4 + bb)) * __ldg(k4 + 15) ==
+                      __ldg(k4 + 15 - a * 4) * __ldg(k4 + 15 - bb));
+    sep_flag = sep ? 1 : 0;
+  }
+  __syncthreads();
   const uint32_t smem0 = smem_u32(tile4);
+  const int qd = tid & 15;
+  const int p0 = tid >> 4;
 
-  auto issue = [&](long long t, int buf) {
-    const BlurTile bt = blur_tile(t, tiles_x, tiles_y, cblocks);
-    const uint32_t dst0 = smem0 + static_cast<uint32_t>(buf) * TILE_ELEMS * 16u;
-    for (int i = tid; i < TILE_ELEMS; i += 256) {
-      const int qd = i & 15;
-      const int pos = i >> 4;
-      const int ly = pos / BF_PW, lx = pos - ly * BF_PW;
-      const int ty = bt.oy0 + ly - 1, tx = bt.ox0 + lx - 1;
-      const bool valid = (ty >= 0 && ty <= Ho && tx >= 0 && tx <= Wo);
-      const float* src = t_cl;
-      if (valid) {
-        const int ph = (ty & 1) * 2 + (tx & 1);
-        const long long row = (static_cast<long long>(bt.b) * Hp_in + (ty >> 1)) * Wp_in + (tx >> 1);
-        src = t_cl + (ph * rows_in + row) * C + bt.c0 + qd * 4;
+  // Staging of one tile = 11 x 19 positions x 16 channel quads.  Thread (lx = tid >> 4, qd) owns
+  // column lx of all 11 rows: the tile origin (8k - 1, 16k - 1) is odd, so the row parity of slot
+  // ly is a compile-time constant and the two phase pointers just advance by one input row every
+  // second slot.  The last 3 columns (33 positions) are spread over the threads afterwards.
+  auto issue = [&](const BlurCoord& tc, int buf) {
+    const int oy0 = tc.d[2] * BF_TY - 1, ox0 = tc.d[1] * BF_TX - 1;
+    const int m = tc.d[2] * (BF_TY / 2);                 // ty = 2m - 1 + ly
+    const int rowb = tc.d[3] * Hp_in;
+    const float* base = t_cl + tc.d[0] * BF_C + qd * 4;
+    const uint32_t tile_s = smem0 + static_cast<uint32_t>(buf) * TILE_ELEMS * 16u;
+    const unsigned rstride = static_cast<unsigned>(Wp_in) * static_cast<unsigned>(C);
+    {
+      const int lx = p0;                                  // 0..15
+      const int tx = ox0 + lx;
+      const bool vx = static_cast<unsigned>(tx) <= static_cast<unsigned>(Wo);
+      const int pb = tx & 1, txh = tx >> 1;
+      // odd rows (ly even): phase 2+pb, input row m-1 + ly/2 ; even rows (ly odd): phase pb, row m + ly/2
+      const unsigned i1 = static_cast<unsigned>((2 + pb) * rows_in + (rowb + m - 1) * Wp_in + txh);
+      const unsigned i0 = static_cast<unsigned>(pb * rows_in + (rowb + m) * Wp_in + txh);
+      const float* p1 = base + static_cast<unsigned long long>(i1) * static_cast<unsigned>(C);
+      const float* pe = base + static_cast<unsigned long long>(i0) * static_cast<unsigned>(C);
+      const uint32_t dst = tile_s + static_cast<uint32_t>(lx * 16 + qd) * 16u;
+#pragma unroll
+      for (int l = 0; l < BF_PH; ++l) {
+        const int ty = oy0 + l;
+        const bool valid = vx && (static_cast<unsigned>(ty) <= static_cast<unsigned>(Ho));
+        const float* src = ((l & 1) ? pe : p1) + static_cast<size_t>(l >> 1) * rstride;
+        const uint32_t d = dst + static_cast<uint32_t>(l * BF_PW * 16) * 16u;
+        if (valid) cp_async16(d, src); else st_shared_zero16(d);
       }
-      cp_async16_zfill(dst0 + static_cast<uint32_t>(i) * 16u, src, valid);
+    }
+#pragma unroll
+    for (int e0 = 0; e0 < 3 * BF_PH * 16; e0 += 256) {     // columns 16..18: 528 quads
+      const int e = e0 + tid;
+      if (e < 3 * BF_PH * 16) {
+        const int r = e >> 4;                              // 0..32 = ly * 3 + (lx - 16)
+        const int l = r / 3, lx = 16 + (r - l * 3);
+        const int ty = oy0 + l, tx = ox0 + lx;
+        const bool valid = (static_cast<unsigned>(ty) <= static_cast<unsigned>(Ho)) &&
+                           (static_cast<unsigned>(tx) <= static_cast<unsigned>(Wo));
+        const unsigned idx = static_cast<unsigned>((((ty & 1) << 1) | (tx & 1)) * rows_in +
+                                                   (rowb + (ty >> 1)) * Wp_in + (tx >> 1));
+        const float* src = base + static_cast<unsigned long long>(idx) * static_cast<unsigned>(C);
+        const uint32_t d = tile_s + static_cast<uint32_t>((l * BF_PW + lx) * 16 + qd) * 16u;
+        if (valid) cp_async16(d, src); else st_shared_zero16(d);
+      }
     }
     cp_async_commit();
   };
 
-  long long t = blockIdx.x;
-  if (t < ntiles) issue(t, 0);
-  const float nw = noise ? __ldg(noise_w) : 0.f;
-  const int qd = tid & 15;
+  unsigned t = blockIdx.x;
+  BlurCoord cur = blur_coord(t, radix);
+  const BlurCoord step = blur_coord(gridDim.x, radix);
+  if (t < ntiles) issue(cur, 0);
+  const float nw = __ldg(noise_w);
   const int grp = tid >> 4;                 // 16 groups of 8 pixels
   const int ly = grp >> 1;
   const int lx0 = (grp & 1) * 8;
+  const bool sep = sep_flag != 0;
   int buf = 0;
   for (; t < ntiles; t += gridDim.x, buf ^= 1) {
-    const long long tn = t + gridDim.x;
-    if (tn < ntiles) {
-      issue(tn, buf ^ 1);
+    BlurCoord nxt = cur;
+    blur_coord_add(nxt, step, radix);
+    if (t + gridDim.x < ntiles) {
+      issue(nxt, buf ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();                         // tile t landed for every thread (and kf on pass 0)
-    const BlurTile bt = blur_tile(t, tiles_x, tiles_y, cblocks);
+    __syncthreads();                         // tile t has landed for every thread
     const float4* tl = tile4 + buf * TILE_ELEMS;
-    const int oy = bt.oy0 + ly;
-    if (oy <= Ho) {
-      const int b = bt.b;
-      const int c = bt.c0 + qd * 4;
-      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (next_scale) sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
-      const size_t out_row0 = (static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1);
+    const int b = cur.d[3];
+    const int oy = cur.d[2] * BF_TY + ly;
+    const int oxb = cur.d[1] * BF_TX + lx0;
+    if (oy <= Ho && oxb <= Wo) {
+      const int c = cur.d[0] * BF_C + qd * 4;
       float4 a[8];
+      if (sep) {
+        // vertical pass over the 11 columns this thread needs, then 4 horizontal taps per output
+        float4 v[11];
 #pragma unroll
-      for (int px = 0; px < 8; ++px) a[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 11; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int fy = 0; fy < 4; ++fy) {
-        float4 tv[11];
+        for (int fy = 0; fy < 4; ++fy) {
+          const float ky = kf[fy * 4];
 #pragma unroll
-        for (int i = 0; i < 11; ++i) tv[i] = tl[((ly + fy) * BF_PW + lx0 + i) * 16 + qd];
+          for (int i = 0; i < 11; ++i) {
+            const float4 tv = tl[((ly + fy) * BF_PW + lx0 + i) * 16 + qd];
+            v[i].x = fmaf(tv.x, ky, v[i].x);
+            v[i].y = fmaf(tv.y, ky, v[i].y);
+            v[i].z = fmaf(tv.z, ky, v[i].z);
+            v[i].w = fmaf(tv.w, ky, v[i].w);
+          }
+        }
+        const float inv = 1.f / kf[0];
+        const float kx0 = 1.f, kx1 = kf[1] * inv, kx2 = kf[2] * inv, kx3 = kf[3] * inv;
 #pragma unroll
-        for (int fx = 0; fx < 4; ++fx) {
-          const float kk = kf[fy * 4 + fx];
+        for (int px = 0; px < 8; ++px) {
+          a[px].x = fmaf(v[px + 3].x, kx3, fmaf(v[px + 2].x, kx2, fmaf(v[px + 1].x, kx1, v[px].x * kx0)));
+          a[px].y = fmaf(v[px + 3].y, kx3, fmaf(v[px + 2].y, kx2, fmaf(v[px + 1].y, kx1, v[px].y * kx0)));
+          a[px].z = fmaf(v[px + 3].z, kx3, fmaf(v[px + 2].z, kx2, fmaf(v[px + 1].z, kx1, v[px].z * kx0)));
+          a[px].w = fmaf(v[px + 3].w, kx3, fmaf(v[px + 2].w, kx2, fmaf(v[px + 1].w, kx1, v[px].w * kx0)));
+        }
+      } else {
 #pragma unroll
-          for (int px = 0; px < 8; ++px) {
-            a[px].x = fmaf(tv[px + fx].x, kk, a[px].x);
-            a[px].y = fmaf(tv[px + fx].y, kk, a[px].y);
-            a[px].z = fmaf(tv[px + fx].z, kk, a[px].z);
-            a[px].w = fmaf(tv[px + fx].w, kk, a[px].w);
+        for (int px = 0; px < 8; ++px) a[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int fy = 0; fy < 4; ++fy) {
+          float4 tv[11];
+#pragma unroll
+          for (int i = 0; i < 11; ++i) tv[i] = tl[((ly + fy) * BF_PW + lx0 + i) * 16 + qd];
+#pragma unroll
+          for (int fx = 0; fx < 4; ++fx) {
+            const float kk = kf[fy * 4 + fx];
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+              a[px].x = fmaf(tv[px + fx].x, kk, a[px].x);
+              a[px].y = fmaf(tv[px + fx].y, kk, a[px].y);
+              a[px].z = fmaf(tv[px + fx].z, kk, a[px].z);
+              a[px].w = fmaf(tv[px + fx].w, kk, a[px].w);
+            }
           }
         }
       }
+      const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
+      const bool rowreal = oy < Ho;
+      const float* nrow = noise + static_cast<size_t>(b) * noise_bstride +
+                          static_cast<size_t>(rowreal ? oy : 0) * Wo;
+      const size_t off0 = ((static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1) + oxb) * C + c;
+      __nv_bfloat16* ph = next_hi + off0;
+      __nv_bfloat16* pl = next_lo + off0;
 #pragma unroll
       for (int px = 0; px < 8; ++px) {
-        const int ox = bt.ox0 + lx0 + px;
+        const int ox = oxb + px;
         if (ox > Wo) break;
-        float4 v = a[px];
-        const bool real = (oy < Ho) && (ox < Wo);
-        if (real) {
-          if (noise) {
-            const float nz = nw * __ldg(noise + static_cast<size_t>(b) * noise_bstride +
-                                        static_cast<size_t>(oy) * Wo + ox);
-            v.x += nz; v.y += nz; v.z += nz; v.w += nz;
-          }
-          v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
-          if (act) {
-            v.x = (v.x > 0.f ? v.x : 0.2f * v.x) * 1.4142135623730951f;
-            v.y = (v.y > 0.f ? v.y : 0.2f * v.y) * 1.4142135623730951f;
-            v.z = (v.z > 0.f ? v.z : 0.2f * v.z) * 1.4142135623730951f;
-            v.w = (v.w > 0.f ? v.w : 0.2f * v.w) * 1.4142135623730951f;
-          }
-          if (y_out) {
-            const size_t hw = static_cast<size_t>(Ho) * Wo;
-            float* yp = y_out + (static_cast<size_t>(b) * C + c) * hw + static_cast<size_t>(oy) * Wo + ox;
-            yp[0] = v.x; yp[hw] = v.y; yp[2 * hw] = v.z; yp[3 * hw] = v.w;
-          }
-        }
-        if (next_hi) {
-          const float k0 = real ? sc.x * v.x : 0.f, k1 = real ? sc.y * v.y : 0.f;
-          const float k2 = real ? sc.z * v.z : 0.f, k3 = real ? sc.w * v.w : 0.f;
+        uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);   // pad row / column: zeros
+        if (rowreal && ox < Wo) {
+          const float nz = nw * __ldg(nrow + ox);
+          float v0 = (a[px].x + nz) + bs.x, v1 = (a[px].y + nz) + bs.y;
+          float v2 = (a[px].z + nz) + bs.z, v3 = (a[px].w + nz) + bs.w;
+          v0 = fmaxf(v0, 0.2f * v0) * 1.4142135623730951f;        // leaky-ReLU(0.2) * sqrt(2)
+          v1 = fmaxf(v1, 0.2f * v1) * 1.4142135623730951f;
+          v2 = fmaxf(v2, 0.2f * v2) * 1.4142135623730951f;
+          v3 = fmaxf(v3, 0.2f * v3) * 1.4142135623730951f;
+          const float k0 = sc.x * v0, k1 = sc.y * v1, k2 = sc.z * v2, k3 = sc.w * v3;
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(k0, k1), h23 = __floats2bfloat162_rn(k2, k3);
-          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-          const __nv_bfloat162 l01 = __floats2bfloat162_rn(k0 - f01.x, k1 - f01.y);
-          const __nv_bfloat162 l23 = __floats2bfloat162_rn(k2 - f23.x, k3 - f23.y);
-          const size_t off = (out_row0 + ox) * C + c;
-          *reinterpret_cast<uint2*>(next_hi + off) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-          *reinterpret_cast<uint2*>(next_lo + off) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+          const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          // bf16 -> fp32 is a 16-bit shift: low half = first element
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(k0 - __uint_as_float(u01 << 16),
+                                                           k1 - __uint_as_float(u01 & 0xffff0000u));
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(k2 - __uint_as_float(u23 << 16),
+                                                           k3 - __uint_as_float(u23 & 0xffff0000u));
+          hv = make_uint2(u01, u23);
+          lv = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         }
+        *reinterpret_cast<uint2*>(ph + static_cast<size_t>(px) * C) = hv;
+        *reinterpret_cast<uint2*>(pl + static_cast<size_t>(px) * C) = lv;
       }
     }
     __syncthreads();                         // buffer `buf` is free for the prefetch of pass +1
+    cur = nxt;
   }
 }
 
@@ -656,40 +747,54 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
 // (ToRGBF's `+ bias + skip` with the skip's UpsampleO = upfirdn2d(up=2, pad=(2,1)) inline;
 //  models.py:435-447,639-655).  3-channel tensors: negligible traffic.
 // ---------------------------------------------------------------------------
-__global__ void rgb_combine_kernel(const float* __restrict__ part, int nparts, int B, int H, int W,
-                                   const float* __restrict__ bias, const float* __restrict__ prev,
-                                   const float* __restrict__ k4, float* __restrict__ out) {
-  const long long total = static_cast<long long>(B) * 3 * H * W;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % W);
-  const int y = static_cast<int>((idx / W) % H);
-  const int bc = static_cast<int>(idx / (static_cast<long long>(W) * H));
-  float acc = 0.f;
-  for (int n = 0; n < nparts; ++n) acc += part[n * total + idx];
-  acc += __ldg(bias + bc % 3);
+// grid (x quads, y, b*3+c), one thread = 4 consecutive x of one row (float4 partial loads / store);
+// no integer division on the index path (the flat-index version spent its time in 64-bit div/mod).
+__global__ void __launch_bounds__(256)
+rgb_combine_kernel(const float* __restrict__ part, int nparts, long long part_stride, int H, int W,
+                   const float* __restrict__ bias, const float* __restrict__ prev,
+                   const float* __restrict__ k4, float* __restrict__ out) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;          // quad index along x
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int bc = blockIdx.z;
+  const int x0 = xq * 4;
+  if (x0 >= W || y >= H) return;
+  const size_t row = (static_cast<size_t>(bc) * H + y) * W + x0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < nparts; ++n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + n * part_stride + row));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float bv = __ldg(bias + bc % 3);
+  acc.x += bv; acc.y += bv; acc.z += bv; acc.w += bv;
   if (prev) {
-    const int h2 = H / 2, w2 = W / 2;
+    // UpsampleO = upfirdn2d(up 2, pad (2,1)): out(y,x) = sum over taps with (y+ky-2), (x+kx-2)
+    // even of prev[(y+ky)/2-1, (x+kx)/2-1] * k4[3-ky][3-kx]: 2 x 2 taps per output.  The four
+    // outputs x0..x0+3 touch prev columns c-1..c+2 (c = x0/2) of two rows.
+    const int h2 = H >> 1, w2 = W >> 1;
+    const int c = x0 >> 1;
     const float* src = prev + static_cast<size_t>(bc) * h2 * w2;
-    float u = 0.f;
-    // zero-insert upsampling: only taps with (y + ky - 2) even hit a sample, i.e. ky = (y&1) + 2j
-    // (2 x 2 taps of the 4 x 4 kernel), at input row (y + ky)/2 - 1
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int ky = (y & 1) + 2 * j;
       const int iy = ((y + ky) >> 1) - 1;
       if (iy < 0 || iy >= h2) continue;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int kx = (x & 1) + 2 * i;
-        const int ix = ((x + kx) >> 1) - 1;
-        if (ix < 0 || ix >= w2) continue;
-        u = fmaf(__ldg(src + iy * w2 + ix), __ldg(k4 + (3 - ky) * 4 + (3 - kx)), u);
-      }
+      const float* r = src + static_cast<size_t>(iy) * w2;
+      const float pm = (c - 1 >= 0) ? __ldg(r + c - 1) : 0.f;
+      const float p0 = __ldg(r + c);
+      const float p1 = (c + 1 < w2) ? __ldg(r + c + 1) : 0.f;
+      const float p2 = (c + 2 < w2) ? __ldg(r + c + 2) : 0.f;
+      const float* kr = k4 + (3 - ky) * 4;
+      const float w0 = __ldg(kr + 0), w1 = __ldg(kr + 1), w2k = __ldg(kr + 2), w3 = __ldg(kr + 3);
+      // even x: kx = 0 -> column 3 of the kernel row, kx = 2 -> column 1; odd x: kx = 1 -> 2, 3 -> 0
+      u.x = fmaf(pm, w3, fmaf(p0, w1, u.x));      // x0   : prev c-1 (kx 0), c   (kx 2)
+      u.y = fmaf(p0, w2k, fmaf(p1, w0, u.y));     // x0+1 : prev c   (kx 1), c+1 (kx 3)
+      u.z = fmaf(p0, w3, fmaf(p1, w1, u.z));      // x0+2 : prev c   (kx 0), c+1 (kx 2)
+      u.w = fmaf(p1, w2k, fmaf(p2, w0, u.w));     // x0+3 : prev c+1 (kx 1), c+2 (kx 3)
     }
-    acc += u;
+    acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
   }
-  out[idx] = acc;
+  *reinterpret_cast<float4*>(out + row) = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -709,47 +814,96 @@ struct StyleJobs {
   int n;
 };
 
-// block = (layer, 8-channel group): the B latent rows of that layer are staged in smem once,
-// each of the 8 warps owns one output channel and reads its weight row once.
+// block = (layer, group of 8*cpw channels): the B latent rows of that layer are staged in smem
+// once (float4), every warp owns cpw output channels; a channel's weight row lives in registers
+// (K <= 512: 16 per lane, loaded once with all loads in flight) and is reused for every batch
+// row, so the kernel is not a chain of dependent weight loads (measured: 24 us -> a few us per
+// mapping layer).
 __global__ void __launch_bounds__(256)
 styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, float scale,
-              float bias_mul, int act, const StyleJobs jobs) {
+              float bias_mul, int act, int cpw, const StyleJobs jobs) {
   extern __shared__ float xs[];            // [B][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int l = 0;
   const int blk = blockIdx.x;
   while (blk >= jobs.first_warp[l + 1]) ++l;          // first_warp holds BLOCK offsets here
-  const int c = (blk - jobs.first_warp[l]) * 8 + warp;
   const float* x0 = latent + static_cast<size_t>(jobs.lat[l]) * K;
-  for (int i = threadIdx.x; i < B * K; i += 256) {
-    const int b = i / K, k = i - b * K;
-    xs[i] = __ldg(x0 + static_cast<size_t>(b) * n_latent * K + k);
+  if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(x0) & 15u) == 0) {
+    const int kq = K >> 2;
+    float4* xs4 = reinterpret_cast<float4*>(xs);
+    for (int i = threadIdx.x; i < B * kq; i += 256) {
+      const int b = i / kq, q = i - b * kq;
+      xs4[i] = __ldg(reinterpret_cast<const float4*>(x0 + static_cast<size_t>(b) * n_latent * K) + q);
+    }
+  } else {
+    for (int i = threadIdx.x; i < B * K; i += 256) {
+      const int b = i / K, k = i - b * K;
+      xs[i] = __ldg(x0 + static_cast<size_t>(b) * n_latent * K + k);
+    }
   }
   __syncthreads();
   const int C = jobs.chans[l];
-  if (c >= C) return;
-  const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
-  const float bv = __ldg(jobs.bias[l] + c) * bias_mul;
   float* out = jobs.out[l];
-  for (int b0 = 0; b0 < B; b0 += 8) {
-    float acc[8];
+  const int nk = (K + 31) >> 5;
+  for (int cc = 0; cc < cpw; ++cc) {
+    const int c = ((blk - jobs.first_warp[l]) * 8 + warp) * cpw + cc;
+    if (c >= C) break;
+    const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
+    const float bv = __ldg(jobs.bias[l] + c) * bias_mul;
+    if (nk <= 16) {
+      float wv[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(wrow + k) * scale;
+      for (int j = 0; j < 16; ++j) {
+        const int k = lane + 32 * j;
+        wv[j] = (k < K) ? __ldg(wrow + k) * scale : 0.f;
+      }
+      for (int b0 = 0; b0 < B; b0 += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* xr[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (b0 + i < B) acc[i] = fmaf(xs[(b0 + i) * K + k], wv, acc[i]);
-    }
+        for (int i = 0; i < 4; ++i) xr[i] = xs + static_cast<size_t>(min(b0 + i, B - 1)) * K;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = acc[i];
+        for (int j = 0; j < 16; ++j) {
+          const int k = lane + 32 * j;
+          if (k < K) {
 #pragma unroll
-      for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == 0 && b0 + i < B) {
-        float v = a + bv;
-        if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;   // fused_leaky_relu
-        out[static_cast<size_t>(b0 + i) * C + c] = v;
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(xr[i][k], wv[j], acc[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = acc[i];
+#pragma unroll
+          for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+          if (lane == 0 && b0 + i < B) {
+            float v = a + bv;
+            if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;   // fused_leaky_relu
+            out[static_cast<size_t>(b0 + i) * C + c] = v;
+          }
+        }
+      }
+    } else {                                  // long rows: stream the weights per 8-row group
+      for (int b0 = 0; b0 < B; b0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+          const float wv = __ldg(wrow + k) * scale;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (b0 + i < B) acc[i] = fmaf(xs[(b0 + i) * K + k], wv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = acc[i];
+#pragma unroll
+          for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+          if (lane == 0 && b0 + i < B) {
+            float v = a + bv;
+            if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
+            out[static_cast<size_t>(b0 + i) * C + c] = v;
+          }
+        }
       }
     }
   }
@@ -775,7 +929,7 @@ __global__ void pixel_norm_kernel(const float* __restrict__ z, int B, int K, flo
 // ---------------------------------------------------------------------------
 // demod_multi: the demodulation factors of EVERY styled conv of the generator in one launch
 // (they only depend on the styles), plus the ToRGB modulated 1x1 weights
-//   kind 0: out[b,o]   = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)        one warp per (b,o)
+//   kind 0: out[b,o]   = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)        one warp per o
 //   kind 1: out[b,c,i] = (wscale * w[c,i]) * style[b,i]   (c < 3; `wsq` holds w) one warp per (b,c)
 // ---------------------------------------------------------------------------
 struct DemodJobs {
@@ -795,27 +949,62 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
   int l = 0;
   const int blk = blockIdx.x;
   while (blk >= jobs.first_block[l + 1]) ++l;
-  const int gw = (blk - jobs.first_block[l]) * 8 + (threadIdx.x >> 5);
+  const int unit = (blk - jobs.first_block[l]) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int Cout = jobs.cout[l], Cin = jobs.cin[l];
-  if (gw >= B * Cout) return;
-  const int b = gw / Cout, o = gw - b * Cout;
-  const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
-  const float* q = jobs.wsq[l] + static_cast<size_t>(o) * Cin;
-  if (jobs.kind[l] == 1) {
+  if (jobs.kind[l] == 1) {                       // unit = (b, c): one modulated ToRGB weight row
+    if (unit >= B * Cout) return;
+    const int b = unit / Cout, o = unit - b * Cout;
+    const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
+    const float* q = jobs.wsq[l] + static_cast<size_t>(o) * Cin;
     const float ws = jobs.wscale[l];
-    float* dst = jobs.out[l] + static_cast<size_t>(gw) * Cin;
+    float* dst = jobs.out[l] + static_cast<size_t>(unit) * Cin;
     for (int i = lane; i < Cin; i += 32) dst[i] = (ws * __ldg(q + i)) * __ldg(s + i);
     return;
   }
-  float acc = 0.f;
-  for (int i = lane; i < Cin; i += 32) {
-    const float sv = __ldg(s + i);
-    acc = fmaf(sv * sv, __ldg(q + i), acc);
-  }
+  // kind 0, unit = output channel o: its wsq row is read ONCE (registers) and reused for every
+  // sample (one warp per (b,o) re-read all of wsq B times from L2: measured 48 us)
+  if (unit >= Cout) return;
+  const int o = unit;
+  const float* q = jobs.wsq[l] + static_cast<size_t>(o) * Cin;
+  float* out = jobs.out[l];
+  const int nk = (Cin + 31) >> 5;
+  if (nk <= 16) {
+    float qv[16];
 #pragma unroll
-  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) jobs.out[l][gw] = rsqrtf(acc + eps);
+    for (int j = 0; j < 16; ++j) {
+      const int i = lane + 32 * j;
+      qv[j] = (i < Cin) ? __ldg(q + i) : 0.f;
+    }
+#pragma unroll 2
+    for (int b = 0; b < B; ++b) {
+      const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = lane + 32 * j;
+        if (i < Cin) {
+          const float sv = __ldg(s + i);
+          acc = fmaf(sv * sv, qv[j], acc);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) out[static_cast<size_t>(b) * Cout + o] = rsqrtf(acc + eps);
+    }
+  } else {
+    for (int b = 0; b < B; ++b) {
+      const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
+      float acc = 0.f;
+      for (int i = lane; i < Cin; i += 32) {
+        const float sv = __ldg(s + i);
+        acc = fmaf(sv * sv, __ldg(q + i), acc);
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) out[static_cast<size_t>(b) * Cout + o] = rsqrtf(acc + eps);
+    }
+  }
 }
 
 inline int grid_for(long long n, int threads, int cap = 148 * 16) {
@@ -956,12 +1145,13 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
     return RW_ERR_BAD_ARG;
   }
   const int tiles_x = (Wo + 1 + BF_TX - 1) / BF_TX, tiles_y = (Ho + 1 + BF_TY - 1) / BF_TY;
-  static int use_pipe = -1;
-  if (use_pipe < 0) {
-    const char* e = getenv("RW_BLUR_PIPE");
-    use_pipe = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (use_pipe) {
+  const long long ntiles = static_cast<long long>(tiles_x) * tiles_y * gz;
+  const long long rows_in4 = 4LL * B * (Hin + 1) * (Win + 1);
+  // the generation fast path's configuration runs the pipelined kernel; anything else (no noise,
+  // no activation, fp32 NCHW output, huge index ranges) the generic one-tile-per-CTA kernel
+  const bool fast = noise && noise_w && bias && act && next_scale && next_hi && next_lo && !y_out &&
+                    ntiles < 0x7fffffffLL && rows_in4 < 0x7fffffffLL;
+  if (fast) {
     static bool attr2 = false;
     if (!attr2) {
       int rc = check_cuda(cudaFuncSetAttribute(blur_up_pipe_kernel,
@@ -971,13 +1161,12 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
       if (rc) return rc;
       attr2 = true;
     }
-    const long long ntiles = static_cast<long long>(tiles_x) * tiles_y * gz;
     long long g = 2LL * device_sm_count();
     if (g > ntiles) g = ntiles;
     blur_up_pipe_kernel<<<static_cast<unsigned>(g), 256, 2 * smem, stream>>>(
-        t_cl, B, C, Hin, Win, k4, noise, noise_bstride, noise_w, bias, act, next_scale,
-        static_cast<__nv_bfloat16*>(next_hi), static_cast<__nv_bfloat16*>(next_lo), y_out, tiles_x,
-        tiles_y, ntiles);
+        t_cl, B, C, Hin, Win, k4, noise, noise_bstride, noise_w, bias, next_scale,
+        static_cast<__nv_bfloat16*>(next_hi), static_cast<__nv_bfloat16*>(next_lo), tiles_x, tiles_y,
+        static_cast<unsigned>(ntiles));
     return check_cuda(cudaGetLastError(), "blur_up_pipe launch");
   }
   dim3 grid(tiles_x, tiles_y, static_cast<unsigned>(gz));
@@ -989,15 +1178,29 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
 
 int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
                        const float* prev, const float* k4, float* out, cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * 3 * H * W;
-  rgb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      part, nparts, B, H, W, bias, prev, k4, out);
+  if ((W & 3) != 0 || (prev && ((H | W) & 1)) || static_cast<long long>(B) * 3 > 65535 ||
+      (reinterpret_cast<uintptr_t>(part) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) {
+    set_last_error("rgb_combine: W=%d must be a multiple of 4 (even H, W with a skip), B*3 <= 65535, "
+                   "16-byte aligned buffers", W);
+    return RW_ERR_BAD_ARG;
+  }
+  const int quads = W / 4;
+  const int bx = quads >= 64 ? 64 : (quads >= 32 ? 32 : (quads >= 16 ? 16 : (quads >= 8 ? 8 : (quads >= 4 ? 4 : (quads >= 2 ? 2 : 1)))));
+  const int by = 256 / bx > H ? H : 256 / bx;
+  dim3 block(bx, by);
+  dim3 grid((quads + bx - 1) / bx, (H + by - 1) / by, B * 3);
+  const long long part_stride = static_cast<long long>(B) * 3 * H * W;
+  rgb_combine_kernel<<<grid, block, 0, stream>>>(part, nparts, part_stride, H, W, bias, prev, k4,
+                                                 out);
   return check_cuda(cudaGetLastError(), "rgb_combine launch");
 }
 
 int styles_launch(const float* latent, int B, int n_latent, int K, float scale, float bias_mul,
                   int act, int n, const float* const* w, const float* const* bias,
                   float* const* out, const int* lat, const int* chans, cudaStream_t stream) {
+  // many layers in one launch: 4 channels per warp (fewer blocks re-staging the same latent rows);
+  // a single layer (mapping network): 1 channel per warp so that 64 SMs share the work
+  const int cpw = (n > 1) ? 4 : 1;
   if (n < 1 || n > 32) {
     set_last_error("styles: %d layers (max 32)", n);
     return RW_ERR_BAD_ARG;
@@ -1012,7 +1215,7 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     jobs.lat[i] = lat[i];
     jobs.chans[i] = chans[i];
     jobs.first_warp[i] = warps;
-    warps += (chans[i] + 7) / 8;          // blocks of 8 channels
+    warps += (chans[i] + 8 * cpw - 1) / (8 * cpw);          // blocks of 8*cpw channels
   }
   jobs.first_warp[n] = warps;
   const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
@@ -1028,7 +1231,8 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     if (rc) return rc;
     attr = smem;
   }
-  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, bias_mul, act, jobs);
+  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, bias_mul, act, cpw,
+                                              jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
 }
 
@@ -1058,7 +1262,7 @@ int demod_multi_launch(int B, float eps, int n, const float* const* style,
     jobs.kind[i] = kind[i];
     jobs.wscale[i] = wscale[i];
     jobs.first_block[i] = blocks;
-    blocks += (B * cout[i] + 7) / 8;
+    blocks += ((kind[i] == 1 ? B * cout[i] : cout[i]) + 7) / 8;
   }
   jobs.first_block[n] = blocks;
   demod_multi_kernel<<<blocks, 256, 0, stream>>>(B, eps, jobs);

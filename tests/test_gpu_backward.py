@@ -87,7 +87,7 @@ def test_blur_adj_phase_equals_materialised_adjoint(B, C, H, W, scaled):
     bt = ops.upfirdn2d_raw(t.reshape(B * C, 2 * H + 1, 2 * W + 1, 1), kern, 1, 1, 1, 1, 1, 1, 1, 1)
     lhs = (bt.view(B, C, 2 * H, 2 * W).double() * g_pre.double()).sum()
     rhs = (t.double() * g_t.double()).sum()
-    assert abs(float(lhs - rhs)) < 1e-6 * max(1.0, abs(float(lhs)))
+    assert abs(float(lhs - rhs)) < 1e-5 * max(1.0, abs(float(lhs)))    # fp32 FIR outputs
     hi2 = torch.empty_like(hi)
     lo2 = torch.empty_like(lo)
     _cabi.call('rw_prep_phase_keys', ops._p(g_t), ops._p(dm), B, C, H, W, ops._p(hi2), ops._p(lo2),

@@ -95,16 +95,22 @@ def test_rgb_combine_vs_oracle_upsample(B, H, W, nparts, has_prev):
     assert (out - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
 
 
-@pytest.mark.parametrize('B,C,H,W', [(2, 64, 4, 4), (1, 128, 5, 7), (3, 64, 16, 16), (2, 128, 33, 9)])
-def test_blur_up_fused_vs_layer_kernels(B, C, H, W):
-    """pipelined persistent blur (channels-last phases in, next-layer planes + NCHW out) ==
-    blur_up_act on the NCHW conv_transpose output -> prep_keys"""
+@pytest.mark.parametrize('separable', [True, False])
+@pytest.mark.parametrize('B,C,H,W', [(2, 64, 4, 4), (1, 128, 5, 7), (3, 64, 16, 16), (2, 128, 33, 9),
+                                     (2, 192, 20, 40)])
+def test_blur_up_fused_vs_layer_kernels(B, C, H, W, separable):
+    """both blur kernels — the generic one (fp32 NCHW output + planes) and the pipelined
+    persistent one the generation fast path launches (planes only; separable and 16-tap FIR) —
+    == blur_up_act on the NCHW conv_transpose output -> prep_keys"""
     from rewriting_b200 import _cabi, ops
     torch.manual_seed(3)
     dev = 'cuda'
     Ht, Wt, Ho, Wo = 2 * H + 1, 2 * W + 1, 2 * H, 2 * W
     t = torch.randn(B, C, Ht, Wt, device=dev)
-    kern = (orc.make_kernel([1, 3, 3, 1]) * 4 + 0.03 * torch.randn(4, 4)).to(dev)
+    kern = orc.make_kernel([1, 3, 3, 1]) * 4
+    if not separable:
+        kern = kern + 0.03 * torch.randn(4, 4)          # asymmetric: also catches a wrong flip
+    kern = kern.to(dev)
     noise = ops.noise_table(B, Ho * Wo, dev)
     nw = torch.tensor([0.37], device=dev)
     bias = torch.randn(C, device=dev)
@@ -118,17 +124,20 @@ def test_blur_up_fused_vs_layer_kernels(B, C, H, W):
             t_cl[a * 2 + b, :, :sub.shape[2], :sub.shape[3]] = sub.permute(0, 2, 3, 1)
     t_cl = t_cl.reshape(4, rows, C).contiguous()
     rows_o = B * (Ho + 1) * (Wo + 1)
-    nh = torch.empty(rows_o, C, dtype=torch.bfloat16, device=dev)
-    nl = torch.empty_like(nh)
-    y = torch.empty(B, C, Ho, Wo, device=dev)
-    _cabi.call('rw_blur_up_fused', ops._p(t_cl), B, C, H, W, ops._p(kern), ops._p(noise),
-               noise.stride(0), ops._p(nw), ops._p(bias), 1, ops._p(nscale), ops._p(nh),
-               ops._p(nl), ops._p(y), ops._stream())
     want = ops.blur_up_act(t, kern, noise, nw, bias, True)
-    assert (y - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
     planes, _ = ops.prep_keys(want, nscale)
-    got = nh.float() + nl.float()
     ref = planes.hi.float() + planes.lo.float()
-    assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
-    v = got.view(B, Ho + 1, Wo + 1, C)
-    assert v[:, Ho].abs().max() == 0 and v[:, :, Wo].abs().max() == 0       # pad row / column
+    for with_y in (True, False):                          # generic kernel / pipelined kernel
+        nh = torch.full((rows_o, C), float('nan'), dtype=torch.bfloat16, device=dev)
+        nl = torch.full_like(nh, float('nan'))
+        y = torch.empty(B, C, Ho, Wo, device=dev) if with_y else None
+        _cabi.call('rw_blur_up_fused', ops._p(t_cl), B, C, H, W, ops._p(kern), ops._p(noise),
+                   noise.stride(0), ops._p(nw), ops._p(bias), 1, ops._p(nscale), ops._p(nh),
+                   ops._p(nl), ops._p(y), ops._stream())
+        if with_y:
+            assert (y - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
+        got = nh.float() + nl.float()
+        assert torch.isfinite(got).all()                  # every row written, pads included
+        assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item()), with_y
+        v = got.view(B, Ho + 1, Wo + 1, C)
+        assert v[:, Ho].abs().max() == 0 and v[:, :, Wo].abs().max() == 0   # pad row / column
