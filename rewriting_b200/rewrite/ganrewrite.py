@@ -441,9 +441,18 @@ class ProgressiveGanRewriter(object):
                 q = q * signs[None, :]
                 return q.permute(1, 0)
             if key_method == 'gandissect':
-                raise NotImplementedError(
-                    "key_method='gandissect' needs RunningQuantile statistics (UI search path, "
-                    'SURVEY.md §8f-2); use zca / svd / mean')
+                # unit-wise keys: score a unit by how unusual its selected values are, with
+                # explicitly counted quantiles as probabilities [ganrewrite.py:375-400]
+                observed = self._masked_observations(imgnum_mask_pairs)
+                all_obs = torch.cat([o for o, _, _ in observed])
+                all_weight = torch.cat([w for _, _, w in observed])
+                rq = self.quantiles_for_units()
+                logscore = -torch.log(1.0 - rq.normalize(all_obs.permute(1, 0))).permute(1, 0)
+                mean_logscore = (logscore * all_weight).sum(0) / all_weight.sum()
+                top_coords = mean_logscore.sort(descending=True)[1][:rank]
+                result = torch.zeros(rank, all_obs.shape[1], device=all_obs.device)
+                result[torch.arange(rank), top_coords] = 1.0
+                return result
             assert key_method in ['svd', 'mean']
             collected = []
             for imgnum, mask in imgnum_mask_pairs:
@@ -561,15 +570,45 @@ class ProgressiveGanRewriter(object):
         return goal_in, goal_out
 
     # ---------------------------------------------------------------------------- UI search
-    def quantiles_for_units(self):
-        raise NotImplementedError('RunningQuantile statistics serve the UI search path '
-                                  '(SURVEY.md §8f-2) and are not built yet')
+    def _flat_context_keys(self, zbatch):
+        outs = self.context_model(zbatch.to(self.device))
+        acts = self.context_acts(outs).detach()
+        return acts.permute(0, 2, 3, 1).reshape(-1, acts.shape[1]), outs
 
-    quantiles_for_covariance_adjusted_directions = quantiles_for_units
+    def quantiles_for_units(self):
+        """Per-unit quantiles of the context keys over zds [ganrewrite.py:554-565]."""
+        if self.unit_rq is None:
+            with pbar.quiet(), torch.no_grad():
+                self.unit_rq = tally.tally_quantile(
+                    lambda zbatch: self._flat_context_keys(zbatch)[0], self.zds,
+                    cachefile=self.rf('unit_rq.npz'))
+        return self.unit_rq
+
+    def quantiles_for_covariance_adjusted_directions(self):
+        """Quantiles of the C^-1-adjusted keys [ganrewrite.py:567-580]."""
+        if self.cad_rq is None:
+            with pbar.quiet(), torch.no_grad():
+                def adjusted(zbatch):
+                    flat, outs = self._flat_context_keys(zbatch)
+                    return self.covariance_adjusted_key(flat, outs)
+                self.cad_rq = tally.tally_quantile(adjusted, self.zds,
+                                                   cachefile=self.rf('unit_cad.npz'))
+        return self.cad_rq
 
     def ranking_for_key(self, key, k=12):
-        raise NotImplementedError('ranking_for_key needs RunningTopK/RunningQuantile '
-                                  '(UI search path, SURVEY.md §8f-2)')
+        """Images of zds whose context keys respond most to `key` (max over positions of the
+        per-position dot product), plus the quantile statistic of all responses — the search
+        behind the UI's "find similar" [ganrewrite.py:582-594].  Returns (image indexes [k],
+        RunningQuantile of depth 1)."""
+        tensorkey = key.to(self.device)[None, :, None, None]
+        with pbar.quiet(), torch.no_grad():
+            def image_max_sel(zbatch):
+                acts = self.context_acts(self.context_model(zbatch.to(self.device)))
+                heatmap = (acts * tensorkey).sum(dim=1)
+                maxmap = heatmap.view(heatmap.shape[0], -1).max(1)[0]
+                return maxmap, heatmap.view(-1)[:, None]
+            topk, rq = tally.tally_topk_and_quantile(image_max_sel, self.zds, k=k)
+        return topk.result()[1], rq
 
     # ---------------------------------------------------------------------------- rendering
     def render_object(self, target_output, obj_area=None, box=None):

@@ -329,13 +329,18 @@ class RunningQuantile(object):
         if self.count == 0:
             return torch.full((self.depth,) + tuple(qshape), float('nan'))
         vals, pos, total = self._weighted_summary()
+        # positions are exact (sums of powers of two); the reference normalises them in fp32
+        # (runningstats.py:556-562) and interpolates in fp64 — same here, so a loaded reference
+        # sketch reads out identically
+        pos = pos.float()
         if old_style:                       # numpy.percentile convention
             pos = pos - pos[:, :1]
             pos = pos / pos[:, -1:]
         else:
-            pos = pos / total
+            pos = pos / total.float()
         q = quantiles.reshape(1, -1).to(device=vals.device, dtype=torch.float64)
-        res = self._interp(q.expand(self.depth, -1).contiguous(), pos.contiguous(), vals.double())
+        res = self._interp(q.expand(self.depth, -1).contiguous(), pos.double().contiguous(),
+                           vals.double())
         return res.to(self.dtype).view((self.depth,) + tuple(qshape))
 
     def percentiles(self, percentiles):
@@ -349,7 +354,7 @@ class RunningQuantile(object):
         assert self.count > 0
         assert data.shape[0] == self.depth
         vals, pos, total = self._weighted_summary()
-        pos = (pos / total).contiguous()
+        pos = (pos.float() / total.float()).double().contiguous()
         x = data.reshape(self.depth, -1).to(device=vals.device, dtype=torch.float64)
         res = self._interp(x.contiguous(), vals.double().contiguous(), pos)
         return res.clamp_(0.0, 1.0).float().to(data.device).view(data.shape)

@@ -1,6 +1,6 @@
 """Batched statistic drivers with .npz caching (API of the reference's `utils/tally.py`,
-hot-path subset): `tally_second_moment`, `tally_mean`, `make_loader`,
-`load_cached_state`, `save_cached_state`.
+hot-path subset): `tally_second_moment`, `tally_mean`, `tally_topk`, `tally_quantile`,
+`tally_topk_and_quantile`, `make_loader`, `load_cached_state`, `save_cached_state`.
 
 `tally_second_moment(compute, dataset, sample_size=None, batch_size=10, cachefile=None)`
 (reference: tally.py:424-443) iterates a DataLoader over the z dataset, calls
@@ -104,3 +104,79 @@ def tally_mean(compute, dataset, sample_size=None, batch_size=10, cachefile=None
     rmean.to_('cpu')
     save_cached_state(cachefile, rmean, args)
     return rmean
+
+
+def tally_topk(compute, dataset, sample_size=None, batch_size=10, k=100, cachefile=None,
+               **kwargs):
+    """Running top-k of every feature over a dataset (reference: tally.py:44-68)."""
+    args = dict(sample_size=sample_size, k=k)
+    cached = load_cached_state(cachefile, args)
+    if cached is not None:
+        return runningstats.RunningTopK(state=cached)
+    rtk = runningstats.RunningTopK(k=k)
+    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    for batch in pbar(loader):
+        rtk.add(call_compute(compute, batch))
+    rtk.to_('cpu')
+    save_cached_state(cachefile, rtk, args)
+    return rtk
+
+
+def tally_quantile(compute, dataset, sample_size=None, batch_size=10, r=4096, cachefile=None,
+                   **kwargs):
+    """Quantile statistics of every unit over a dataset; `compute` returns (sample, unit)
+    batches (reference: tally.py:134-155).  `r` keys the cache like the reference's."""
+    args = dict(sample_size=sample_size, r=r)
+    cached = load_cached_state(cachefile, args)
+    if cached is not None:
+        return runningstats.RunningQuantile(state=cached)
+    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    rq = runningstats.RunningQuantile()
+    for batch in pbar(loader):
+        rq.add(call_compute(compute, batch))
+    rq.to_('cpu')
+    save_cached_state(cachefile, rq, args)
+    return rq
+
+
+class _Combined(object):
+    """state_dict of several statistics under name prefixes (reference CombinedState,
+    tally.py:650-700: keys `<name>.<key>`)."""
+
+    def __init__(self, **parts):
+        self.parts = parts
+
+    def state_dict(self):
+        out = {}
+        for name, obj in self.parts.items():
+            for k, v in obj.state_dict().items():
+                out['%s.%s' % (name, k)] = v
+        return out
+
+    @staticmethod
+    def split(dat, name):
+        pre = name + '.'
+        return {k[len(pre):]: dat[k] for k in dat.keys() if k.startswith(pre)}
+
+
+def tally_topk_and_quantile(compute, dataset, sample_size=None, batch_size=10, k=100, r=4096,
+                            cachefile=None, **kwargs):
+    """One pass for both: `compute` returns (topk sample, quantile sample) (reference:
+    tally.py:158-180; its cached branch returns an undefined attribute — here both branches
+    return (RunningTopK, RunningQuantile))."""
+    args = dict(sample_size=sample_size, k=k, r=r)
+    cached = load_cached_state(cachefile, args)
+    if cached is not None:
+        return (runningstats.RunningTopK(state=_Combined.split(cached, 'rtk')),
+                runningstats.RunningQuantile(state=_Combined.split(cached, 'rq')))
+    rtk = runningstats.RunningTopK(k=k)
+    rq = runningstats.RunningQuantile(r=r)
+    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    for batch in pbar(loader):
+        sample_tk, sample_q = call_compute(compute, batch)
+        rtk.add(sample_tk)
+        rq.add(sample_q)
+    rtk.to_('cpu')
+    rq.to_('cpu')
+    save_cached_state(cachefile, _Combined(rtk=rtk, rq=rq), args)
+    return rtk, rq
