@@ -95,7 +95,14 @@ __device__ __forceinline__ void decode_tile(int tile, int nphase, int nsched, in
   if (nphase > 1) ph = (ph + ((nsched % nphase) == 0 ? tile / nsched : mn)) % nphase;
 }
 
-template <int BN, int CG>
+// EPI = 0: full fused epilogue (demod, noise, bias, leaky-ReLU, NCHW / channels-last store, next
+//          layer's planes, ToRGB partials — every feature a run-time switch).
+// EPI = 1: lean epilogue — optional per-(b,o) scale and the store, nothing else.  The up-path
+//          conv_transpose phases, dgrad and the plain row-GEMM use it: with 1-4 taps per tile the
+//          mainloop is short, and the generic epilogue's ~37 predicated instructions per column
+//          (2400 per tile and warp) made the MMA issuer wait for TMEM (ncu, layer 13: issuer
+//          spinning on tmem_empty, tensor pipe 52 %).
+template <int BN, int CG, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
@@ -298,73 +305,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       }
 
       // ---- fused epilogue -------------------------------------------------------------
-      // Per-column parameters (demod / bias / next style / ToRGB weights) are read as two
-      // coalesced lane vectors per tile (columns lane and lane+32 of this warp's 64) and handed
-      // out by shuffle.  One load per column made every FMUL wait for its own L1/L2 round trip
-      // (ncu, layer 13: 64 serialised loads = ~14 k cycles per tile, the MMA issuer spinning on
-      // tmem_empty, tensor pipe 52 %).  The shuffles need the whole warp, so the arithmetic
-      // runs for every lane and only the stores are predicated; a warp whose 32 rows straddle
-      // two images (1 in ~500) falls back to per-lane loads.
-      constexpr uint32_t kFull = 0xffffffffu;
-      const bool inrows = prow < p.rows;
-      const int b0 = __shfl_sync(kFull, b, 0);
-      const bool uni = __all_sync(kFull, !inrows || b == b0);
-      const bool lanevec = uni && (b0 < p.B);
-      const int bl = inrows ? b : 0;                         // per-lane sample for the fallback
-      const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(bl) * p.Cout + n0 : nullptr;
-      const float* nsl = p.next_scale ? p.next_scale + static_cast<size_t>(bl) * p.Cout + n0 : nullptr;
-      const float* rwl = p.rgb_w ? p.rgb_w + (static_cast<size_t>(bl) * 3) * p.Cout + n0 : nullptr;
-      float sclv[2] = {1.f, 1.f}, biasv[2] = {0.f, 0.f}, nsv[2] = {0.f, 0.f};
-      float rwv[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      const float* scl = p.scale_bo ? p.scale_bo + static_cast<size_t>(b) * p.Cout : nullptr;
+      if constexpr (EPI == 1) {
+        if (scl != nullptr && prow < p.rows) {
+          const float4* s4 = reinterpret_cast<const float4*>(scl + n0);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int col = hh * 32 + lane;
-        if (p.bias) biasv[hh] = __ldg(p.bias + n0 + col);
-        if (lanevec) {
-          const size_t bo = static_cast<size_t>(b0) * p.Cout + n0 + col;
-          if (p.scale_bo) sclv[hh] = __ldg(p.scale_bo + bo);
-          if (p.next_scale) nsv[hh] = __ldg(p.next_scale + bo);
-          if (p.rgb_w) {
-#pragma unroll
-            for (int c3 = 0; c3 < 3; ++c3)
-              rwv[c3][hh] = __ldg(p.rgb_w + (static_cast<size_t>(b0) * 3 + c3) * p.Cout + n0 + col);
+          for (int j4 = 0; j4 < kEpiCols / 4; ++j4) {
+            const float4 sv = __ldg(s4 + j4);
+            acc[4 * j4] *= sv.x;
+            acc[4 * j4 + 1] *= sv.y;
+            acc[4 * j4 + 2] *= sv.z;
+            acc[4 * j4 + 3] *= sv.w;
           }
         }
-      }
-      float nz = 0.f;
-      if (valid && p.noise != nullptr)
-        nz = __ldg(p.noise_w) * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
-                                      static_cast<size_t>(yy) * Wv + xx);
-      float* outp = p.out;
-      if (valid && p.out != nullptr && p.out_mode == 0)
-        outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
-               static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (p.out_mode == 0 && valid) {
+          float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
+                        static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx +
+                        static_cast<size_t>(n0) * p.out_sc;
 #pragma unroll
-      for (int j = 0; j < kEpiCols; ++j) {
-        float t = acc[j];
-        if (p.scale_bo) t *= lanevec ? __shfl_sync(kFull, sclv[j >> 5], j & 31) : __ldg(scl + j);
-        t += nz;
-        if (p.bias) t += __shfl_sync(kFull, biasv[j >> 5], j & 31);
-        if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
-        acc[j] = t;
-        if (valid && p.out != nullptr && p.out_mode == 0)
-          outp[static_cast<size_t>(n0 + j) * p.out_sc] = t;
-        if (p.rgb_w) {
-          r0 = fmaf(lanevec ? __shfl_sync(kFull, rwv[0][j >> 5], j & 31) : __ldg(rwl + j), t, r0);
-          r1 = fmaf(lanevec ? __shfl_sync(kFull, rwv[1][j >> 5], j & 31) : __ldg(rwl + p.Cout + j), t, r1);
-          r2 = fmaf(lanevec ? __shfl_sync(kFull, rwv[2][j >> 5], j & 31) : __ldg(rwl + 2 * p.Cout + j), t, r2);
+          for (int j = 0; j < kEpiCols; ++j) outp[static_cast<size_t>(j) * p.out_sc] = acc[j];
         }
-      }
-      if (valid && p.rgb_w) {
-        // one partial per 64-channel group: rgb_part[(n_tile*2 + half)][b][c][y*Wv+x]
-        const size_t hw = static_cast<size_t>(Hv) * Wv;
-        float* rp = p.rgb_part +
-                    ((static_cast<size_t>((mn % n_tiles) * 2 + half) * p.B + b) * 3) * hw +
-                    static_cast<size_t>(yy) * Wv + xx;
-        rp[0] = r0;
-        rp[hw] = r1;
-        rp[2 * hw] = r2;
+      } else if (valid) {
+        float nz = 0.f;
+        if (p.noise != nullptr)
+          nz = __ldg(p.noise_w) * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride +
+                                        static_cast<size_t>(yy) * Wv + xx);
+        float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
+                      static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
+        const float* rw0 = p.rgb_w ? p.rgb_w + (static_cast<size_t>(b) * 3) * p.Cout : nullptr;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kEpiCols; ++j) {
+          const int o = n0 + j;
+          float t = acc[j];
+          if (scl) t *= __ldg(scl + o);
+          t += nz;
+          if (p.bias) t += __ldg(p.bias + o);
+          if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
+          acc[j] = t;
+          if (p.out != nullptr && p.out_mode == 0) outp[static_cast<size_t>(o) * p.out_sc] = t;
+          if (rw0) {
+            r0 = fmaf(__ldg(rw0 + o), t, r0);
+            r1 = fmaf(__ldg(rw0 + p.Cout + o), t, r1);
+            r2 = fmaf(__ldg(rw0 + 2 * p.Cout + o), t, r2);
+          }
+        }
+        if (rw0) {
+          // one partial per 64-channel group: rgb_part[(n_tile*2 + half)][b][c][y*Wv+x]
+          const size_t hw = static_cast<size_t>(Hv) * Wv;
+          float* rp = p.rgb_part +
+                      ((static_cast<size_t>((mn % n_tiles) * 2 + half) * p.B + b) * 3) * hw +
+                      static_cast<size_t>(yy) * Wv + xx;
+          rp[0] = r0;
+          rp[hw] = r1;
+          rp[2 * hw] = r2;
+        }
+      } else if (p.out_mode == 1 && prow < p.rows && scl) {
+        // channels-last raw rows are written for every row (pad rows are never read back)
+#pragma unroll
+        for (int j = 0; j < kEpiCols; ++j) acc[j] *= __ldg(scl + n0 + j);
       }
       // Row-per-lane registers -> global through a warp-private smem transpose, so that every
       // store instruction covers whole 64-byte row segments (8 rows x 64 B) instead of
@@ -391,7 +390,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           __syncwarp();
         }
       }
-      if (p.next_hi != nullptr) {
+      if (EPI == 0 && p.next_hi != nullptr) {
+        const float* ns = p.next_scale + static_cast<size_t>(valid ? b : 0) * p.Cout + n0;
 #pragma unroll
         for (int part = 0; part < kEpiCols / 32; ++part) {      // 32 channels = 64 B per pass
 #pragma unroll
@@ -402,11 +402,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = part * 32 + j8 * 8 + 2 * e;
-                const float s0 = lanevec ? __shfl_sync(kFull, nsv[j >> 5], j & 31) : __ldg(nsl + j);
-                const float s1 = lanevec ? __shfl_sync(kFull, nsv[(j + 1) >> 5], (j + 1) & 31)
-                                         : __ldg(nsl + j + 1);
-                const float k0 = valid ? s0 * acc[j] : 0.f;
-                const float k1 = valid ? s1 * acc[j + 1] : 0.f;
+                const float k0 = valid ? __ldg(ns + j) * acc[j] : 0.f;
+                const float k1 = valid ? __ldg(ns + j + 1) * acc[j + 1] : 0.f;
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(k0, k1);
                 if (plane == 0) {
                   w[e] = *reinterpret_cast<const uint32_t*>(&hh);
@@ -449,7 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 
 }  // namespace
 
-template <int CG>
+template <int CG, int EPI>
 static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void* a_lo,
                              const void* w_hi, const void* w_lo, int wk_total,
                              cudaStream_t stream) {
@@ -467,7 +464,7 @@ static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void
   using S = ConvSmem<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, CG>,
+    rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, CG, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
                     "conv_tc smem attr");
     if (rc) return rc;
@@ -492,10 +489,11 @@ static int conv_tc_launch_cg(const ConvTcParams& p, const void* a_hi, const void
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if constexpr (CG == 1) {
-    conv_tc_kernel<BN, 1><<<sched, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    conv_tc_kernel<BN, 1, EPI><<<sched, kNumThreads, S::kTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo,
+                                                                          p);
     return check_cuda(cudaGetLastError(), "conv_tc launch");
   }
-  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CG>, ma_hi, ma_lo, mw_hi, mw_lo, p),
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CG, EPI>, ma_hi, ma_lo, mw_hi, mw_lo, p),
                     "conv_tc launch");
 }
 
@@ -527,8 +525,15 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
     const long long tiles256 = ((static_cast<long long>(p.rows) + 255) / 256) * (p.Cout / BN) * p.nphase;
     cg = (tiles256 >= device_sm_count() / 2) ? 2 : 1;
   }
-  if (cg == 2) return conv_tc_launch_cg<2>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
-  return conv_tc_launch_cg<1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  // lean epilogue when only the optional scale and the store are asked for
+  const bool lean = !p.noise && !p.bias && !p.act && !p.rgb_w && !p.rgb_part && !p.next_hi &&
+                    p.out != nullptr && (reinterpret_cast<uintptr_t>(p.scale_bo) & 15u) == 0;
+  if (cg == 2) {
+    if (lean) return conv_tc_launch_cg<2, 1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+    return conv_tc_launch_cg<2, 0>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  }
+  if (lean) return conv_tc_launch_cg<1, 1>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
+  return conv_tc_launch_cg<1, 0>(p, a_hi, a_lo, w_hi, w_lo, wk_total, stream);
 }
 
 }  // namespace rw

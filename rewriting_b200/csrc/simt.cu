@@ -929,7 +929,7 @@ __global__ void pixel_norm_kernel(const float* __restrict__ z, int B, int K, flo
 // ---------------------------------------------------------------------------
 // demod_multi: the demodulation factors of EVERY styled conv of the generator in one launch
 // (they only depend on the styles), plus the ToRGB modulated 1x1 weights
-//   kind 0: out[b,o]   = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)        one warp per o
+//   kind 0: out[b,o]   = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + eps)        one warp per (o, 8 samples)
 //   kind 1: out[b,c,i] = (wscale * w[c,i]) * style[b,i]   (c < 3; `wsq` holds w) one warp per (b,c)
 // ---------------------------------------------------------------------------
 struct DemodJobs {
@@ -962,10 +962,14 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
     for (int i = lane; i < Cin; i += 32) dst[i] = (ws * __ldg(q + i)) * __ldg(s + i);
     return;
   }
-  // kind 0, unit = output channel o: its wsq row is read ONCE (registers) and reused for every
-  // sample (one warp per (b,o) re-read all of wsq B times from L2: measured 48 us)
-  if (unit >= Cout) return;
-  const int o = unit;
+  // kind 0, unit = (output channel o, group of 8 samples): the wsq row is read once into
+  // registers and reused for the group's samples.  (One warp per (b,o) re-read all of wsq B
+  // times from L2: 48 us; one warp per o walking all B samples serially: 70 us.)
+  const int nbg = (B + 7) >> 3;
+  if (unit >= Cout * nbg) return;
+  const int o = unit / nbg;
+  const int b_lo = (unit - o * nbg) * 8;
+  const int b_hi = min(B, b_lo + 8);
   const float* q = jobs.wsq[l] + static_cast<size_t>(o) * Cin;
   float* out = jobs.out[l];
   const int nk = (Cin + 31) >> 5;
@@ -977,7 +981,7 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
       qv[j] = (i < Cin) ? __ldg(q + i) : 0.f;
     }
 #pragma unroll 2
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
       const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
       float acc = 0.f;
 #pragma unroll
@@ -993,7 +997,7 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
       if (lane == 0) out[static_cast<size_t>(b) * Cout + o] = rsqrtf(acc + eps);
     }
   } else {
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
       const float* s = jobs.style[l] + static_cast<size_t>(b) * Cin;
       float acc = 0.f;
       for (int i = lane; i < Cin; i += 32) {
@@ -1262,7 +1266,7 @@ int demod_multi_launch(int B, float eps, int n, const float* const* style,
     jobs.kind[i] = kind[i];
     jobs.wscale[i] = wscale[i];
     jobs.first_block[i] = blocks;
-    blocks += ((kind[i] == 1 ? B * cout[i] : cout[i]) + 7) / 8;
+    blocks += ((kind[i] == 1 ? B * cout[i] : cout[i] * ((B + 7) / 8)) + 7) / 8;
   }
   jobs.first_block[n] = blocks;
   demod_multi_kernel<<<blocks, 256, 0, stream>>>(B, eps, jobs);

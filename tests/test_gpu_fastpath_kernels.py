@@ -138,6 +138,7 @@ def test_blur_up_fused_vs_layer_kernels(B, C, H, W, separable):
             assert (y - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
         got = nh.float() + nl.float()
         assert torch.isfinite(got).all()                  # every row written, pads included
-        assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item()), with_y
+        # hi + lo reconstructs each side to 2^-17 relative; the two sides may round differently
+        assert (got - ref).abs().max().item() < 3e-5 * max(1.0, ref.abs().max().item()), with_y
         v = got.view(B, Ho + 1, Wo + 1, C)
         assert v[:, Ho].abs().max() == 0 and v[:, :, Wo].abs().max() == 0   # pad row / column

@@ -495,3 +495,41 @@ def test_bulk_sampling_matches_reference_seed_rule(cuda_model, seeded_sd):
                                  reference_count=False)
     want = (imgs[0:2] * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)
     assert u8.shape == (2, 3, 256, 256) and (u8.int() - want.int()).abs().max().item() <= 1
+
+
+def test_ui_search_ranking_and_unit_quantiles_vs_oracle(cuda_model, z40, golden, seeded_sd):
+    """ranking_for_key / quantiles_for_units / key_method='gandissect' (ganrewrite.py:375-400,
+    554-594) on the device against the same statistics computed from the CPU oracle's keys."""
+    from rewriting_b200.rewrite import ganrewrite
+    zds = torch.utils.data.TensorDataset(z40)
+    gw = ganrewrite.SeqStyleGanRewriter(cuda_model, zds, 8)
+    d = torch.from_numpy(golden['d'])[0]
+    sel, rq = gw.ranking_for_key(d.cuda(), k=6)
+    with torch.no_grad():
+        keys = torch.cat([orc.generator_forward(seeded_sd, z40[i:i + 10], upto_key_layer=8)
+                          for i in range(0, 40, 10)])                # [40,512,32,32] oracle keys
+    heat = (keys * d[None, :, None, None]).sum(1).reshape(40, -1)
+    want_sel = heat.max(1)[0].topk(6)[1]
+    assert sel.shape == (6,) and sorted(sel.tolist()) == sorted(want_sel.tolist())
+    assert rq.size() == 40 * 1024
+    qs = [0.01, 0.5, 0.99, 0.999]
+    want_q = torch.quantile(heat.reshape(-1).double(), torch.tensor(qs, dtype=torch.float64))
+    got_q = rq.quantiles(qs)[0].double().cpu()
+    assert (got_q - want_q).abs().max().item() < 2e-3 * max(1.0, want_q.abs().max().item())
+    urq = gw.quantiles_for_units()
+    assert urq.depth == 512 and urq.size() == 40 * 1024
+    flat = keys.permute(0, 2, 3, 1).reshape(-1, 512)
+    med = flat.median(dim=0)[0]
+    assert (urq.median().cpu() - med).abs().max().item() < 2e-3 * max(1.0, med.abs().max().item())
+    one_hot = gw.multi_key_from_selection([(5, golden_mask())], rank=2, key_method='gandissect')
+    assert one_hot.shape == (2, 512) and one_hot.sum().item() == 2 and (one_hot.sum(1) == 1).all()
+
+
+def golden_mask():
+    import base64, io
+    from PIL import Image, ImageDraw
+    im = Image.new('RGBA', (256, 256), (0, 0, 0, 0))
+    ImageDraw.Draw(im).ellipse([70, 80, 130, 120], fill=(255, 255, 255, 255))
+    buf = io.BytesIO()
+    im.save(buf, format='png')
+    return 'data:image/png;base64,' + base64.b64encode(buf.getvalue()).decode('ascii')
