@@ -519,8 +519,11 @@ def test_ui_search_ranking_and_unit_quantiles_vs_oracle(cuda_model, z40, golden,
     urq = gw.quantiles_for_units()
     assert urq.depth == 512 and urq.size() == 40 * 1024
     flat = keys.permute(0, 2, 3, 1).reshape(-1, 512)
-    med = flat.median(dim=0)[0]
-    assert (urq.median().cpu() - med).abs().max().item() < 2e-3 * max(1.0, med.abs().max().item())
+    # rank-space check (a unit whose two middle samples lie far apart has no well-defined value)
+    got_med = urq.median().cpu()
+    rank = (flat <= got_med[None, :] + 1e-3).float().mean(0)
+    rank_lo = (flat <= got_med[None, :] - 1e-3).float().mean(0)
+    assert (rank >= 0.5 - 1e-3).all() and (rank_lo <= 0.5 + 1e-3).all()
     one_hot = gw.multi_key_from_selection([(5, golden_mask())], rank=2, key_method='gandissect')
     assert one_hot.shape == (2, 512) and one_hot.sum().item() == 2 and (one_hot.sum(1) == 1).all()
 
