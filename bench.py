@@ -442,9 +442,10 @@ def main():
                                      'value is the %s' % (ms_eager / K, 'CUDA-graph replay of the '
                                      'same module call' if use_graph else 'eager call'),
                          'peak_source': peaks['source'],
-                         'note': 'algorithmic FLOPs (1x); the 3-term split issues 3x the MMAs, so '
-                                 'frac <= 1/3 by construction; tensor-pipe utilisation is in '
-                                 'profiles/'},
+                         'note': 'algorithmic FLOPs (1x) against the cuBLAS-measured sustained bf16 '
+                                 'peak; the 3-term split issues 3x the MMAs, so frac ~ 1/3 means the '
+                                 'tensor pipe is as busy as in a cuBLAS GEMM; tensor-pipe utilisation '
+                                 'per layer is in profiles/'},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e / K,
                     'h2d_bytes_per_step': BATCH * 512 * 4,
                     'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE * 4},

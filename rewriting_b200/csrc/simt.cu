@@ -504,6 +504,9 @@ blur_up_fused_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(dst), "f"(0.f) : "memory");
 }
@@ -555,6 +558,10 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
   extern __shared__ float4 tile4[];      // 2 x [BF_NPOS][16 quads]
   __shared__ float kf[16];
   __shared__ int sep_flag;
+  // per-tile side data, staged with the tile so that the filter phase issues no global load
+  // (ncu: the 8 noise loads per thread, each consumed at once, were the top stall):
+  // [0,128) noise of the 8 x 16 outputs, [128,192) bias, [192,256) next-layer style
+  __shared__ __align__(16) float side[2][256];
   constexpr int TILE_ELEMS = BF_NPOS * 16;
   const int Ho = 2 * H, Wo = 2 * W;
   const int Hp_in = H + 1, Wp_in = W + 1;
@@ -621,6 +628,24 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
         const float* src = base + static_cast<unsigned long long>(idx) * static_cast<unsigned>(C);
         const uint32_t d = tile_s + static_cast<uint32_t>((l * BF_PW + lx) * 16 + qd) * 16u;
         if (valid) cp_async16(d, src); else st_shared_zero16(d);
+      }
+    }
+    {
+      const uint32_t side_s = smem_u32(&side[buf][0]);
+      if (tid < BF_TY * BF_TX) {
+        const int oy = tc.d[2] * BF_TY + (tid >> 4), ox = tc.d[1] * BF_TX + (tid & 15);
+        if (oy < Ho && ox < Wo)
+          cp_async4(side_s + tid * 4u, noise + static_cast<size_t>(tc.d[3]) * noise_bstride +
+                                           static_cast<size_t>(oy) * Wo + ox);
+        else
+          side[buf][tid] = 0.f;
+      } else if (tid < BF_TY * BF_TX + 16) {
+        const int q4 = (tid - BF_TY * BF_TX) * 4;
+        cp_async16(side_s + (128 + q4) * 4u, bias + tc.d[0] * BF_C + q4);
+      } else if (tid < BF_TY * BF_TX + 32) {
+        const int q4 = (tid - BF_TY * BF_TX - 16) * 4;
+        cp_async16(side_s + (192 + q4) * 4u,
+                   next_scale + static_cast<size_t>(tc.d[3]) * C + tc.d[0] * BF_C + q4);
       }
     }
     cp_async_commit();
@@ -700,11 +725,10 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
           }
         }
       }
-      const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(next_scale + static_cast<size_t>(b) * C + c));
+      const float4 bs = *reinterpret_cast<const float4*>(&side[buf][128 + qd * 4]);
+      const float4 sc = *reinterpret_cast<const float4*>(&side[buf][192 + qd * 4]);
       const bool rowreal = oy < Ho;
-      const float* nrow = noise + static_cast<size_t>(b) * noise_bstride +
-                          static_cast<size_t>(rowreal ? oy : 0) * Wo;
+      const float* nrow = &side[buf][ly * BF_TX + lx0];
       const size_t off0 = ((static_cast<size_t>(b) * (Ho + 1) + oy) * (Wo + 1) + oxb) * C + c;
       __nv_bfloat16* ph = next_hi + off0;
       __nv_bfloat16* pl = next_lo + off0;
@@ -714,7 +738,7 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
         if (ox > Wo) break;
         uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);   // pad row / column: zeros
         if (rowreal && ox < Wo) {
-          const float nz = nw * __ldg(nrow + ox);
+          const float nz = nw * nrow[px];
           float v0 = (a[px].x + nz) + bs.x, v1 = (a[px].y + nz) + bs.y;
           float v2 = (a[px].z + nz) + bs.z, v3 = (a[px].w + nz) + bs.w;
           v0 = fmaxf(v0, 0.2f * v0) * 1.4142135623730951f;        // leaky-ReLU(0.2) * sqrt(2)
@@ -1154,7 +1178,8 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
   // the generation fast path's configuration runs the pipelined kernel; anything else (no noise,
   // no activation, fp32 NCHW output, huge index ranges) the generic one-tile-per-CTA kernel
   const bool fast = noise && noise_w && bias && act && next_scale && next_hi && next_lo && !y_out &&
-                    ntiles < 0x7fffffffLL && rows_in4 < 0x7fffffffLL;
+                    ntiles < 0x7fffffffLL && rows_in4 < 0x7fffffffLL &&
+                    ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(next_scale)) & 15u) == 0;
   if (fast) {
     static bool attr2 = false;
     if (!attr2) {
