@@ -154,9 +154,37 @@ def cpu_baseline_generator(seconds=12.0, batch=2):
             if time.time() - t0 > seconds or n >= 64:
                 break
         dt = time.time() - t0
-    return dict(value=batch * n / dt, unit='images/s', cores=cores, kind='port',
-                sample='%d forwards of batch %d (%.1f s), oracle/sg2_oracle.py generator_forward, '
-                       'torch CPU fp32, %d threads' % (n, batch, dt, cores))
+    out = dict(value=batch * n / dt, unit='images/s', cores=cores, kind='port',
+               sample='%d forwards of batch %d (%.1f s), oracle/sg2_oracle.py generator_forward, '
+                      'torch CPU fp32, %d threads' % (n, batch, dt, cores))
+    # the other two quantities bench `extra` reports, on bounded samples:
+    # key covariance (context forward to layer 8 + second moment) and the rewrite loop
+    try:
+        with torch.no_grad():
+            t0 = time.time()
+            zc = zdataset.standard_z_sample(4, 512, seed=1)
+            keys = [orc.generator_forward(sd, zc[i:i + 2], upto_key_layer=8) for i in (0, 2)]
+            orc.second_moment(keys)
+            dt_cov = time.time() - t0
+        k = keys[0][:1, :, 10:18, 12:21].contiguous()
+        style = torch.ones(1, 512)
+        w = sd['layer8.sconv.mconv.dconv.weight'].clone()
+        tgt = orc.target_forward(k, style, w, sd['layer8.sconv.noise.weight'],
+                                 sd['layer8.sconv.activate.bias']) * 1.5 + 0.3
+        q, _ = torch.linalg.qr(torch.randn(512, 1))
+        its = 10
+        t0 = time.time()
+        orc.insert_loop(w, k, style, tgt, sd['layer8.sconv.noise.weight'],
+                        sd['layer8.sconv.activate.bias'], q.t().contiguous(), its)
+        dt_ins = time.time() - t0
+        out['extra'] = {'key_covariance_samples_per_s': 4 / dt_cov,
+                        'insert_its_per_s': its / dt_ins,
+                        'sample': '4 z to layer 8 + second moment (%.1f s); %d insert iterations on '
+                                  'a 1x512x8x9 key (%.1f s); same oracle port, %d threads'
+                                  % (dt_cov, its, dt_ins, cores)}
+    except Exception as e:  # noqa: BLE001
+        out['extra'] = {'error': '%s: %s' % (type(e).__name__, e)}
+    return out
 
 
 def run_reference(args):

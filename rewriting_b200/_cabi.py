@@ -134,10 +134,16 @@ LAUNCHES_PER_CALL = {
 launch_count = 0
 
 
+_FN = {}
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and raise RwError on a non-zero status."""
     global launch_count
-    lib = load()
-    rc = getattr(lib, name)(*args)
-    check(rc, name)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc, name)
     launch_count += LAUNCHES_PER_CALL.get(name, 1)
