@@ -306,8 +306,9 @@ def main():
     # ---- public API objects: eager module and its CUDA-graph replay -------------------------
     from rewriting_b200.graphs import GraphedModule
     use_graph = not args.no_graph
-    launches0 = _cabi.launch_count
     with torch.no_grad():
+        model(z_dev[:BATCH])                               # one-off weight-plane preparation
+        launches0 = _cabi.launch_count
         model(z_dev[:BATCH])
     launches_per_step = _cabi.launch_count - launches0     # kernels of ONE forward (mine only)
     runner = GraphedModule(model, z_dev[:BATCH]) if use_graph else model
