@@ -231,6 +231,68 @@ def projected_conv(weight, direction):
 
 
 # ---------------------------------------------------------------------------------------
+# UI search and erase statistics (ganrewrite.py:453-496,541-594)
+# ---------------------------------------------------------------------------------------
+def flat_keys(keys):
+    """[B,C,H,W] -> [B*H*W, C] (the `flattened` of ganrewrite.py:546,560)."""
+    return keys.permute(0, 2, 3, 1).reshape(-1, keys.shape[1])
+
+
+def ranking_for_key(keys, key, k=12):
+    """ranking_for_key (ganrewrite.py:582-594): per-image maximum of the key response and the
+    flat list of all responses.  Returns (image indexes of the k largest maxima, responses)."""
+    heat = (keys * key[None, :, None, None]).sum(dim=1)
+    maxmap = heat.reshape(heat.shape[0], -1).max(1)[0]
+    return maxmap.topk(k)[1], heat.reshape(-1)
+
+
+def square_scales_for_units(key_batches):
+    """square_scales_for_units (ganrewrite.py:541-552): running mean of key^2 per unit, merged
+    batch by batch like the reference's RunningVariance.mean()."""
+    count, mean = 0, None
+    for kb in key_batches:
+        a = flat_keys(kb).pow(2)
+        bm = a.sum(0) / a.shape[0]
+        if mean is None:
+            count, mean = a.shape[0], bm
+        else:
+            count += a.shape[0]
+            mean = mean + (bm - mean) * (a.shape[0] / count)
+    return mean
+
+
+def normdissect_units(obs_list, weight_list, square_scale, rank):
+    """normdissect_units (ganrewrite.py:453-471): units whose squared, scale-normalised
+    activation is largest on the selected positions."""
+    all_obs, all_w = torch.cat(obs_list), torch.cat(weight_list)
+    score = all_obs.pow(2) / square_scale[None, :]
+    mean_score = (score * all_w).sum(0) / all_w.sum()
+    return mean_score.sort(descending=True)[1][:rank]
+
+
+def gandissect_units(obs_list, weight_list, sorted_units, rank):
+    """key_method='gandissect' (ganrewrite.py:375-400) with EXACT quantiles: `sorted_units`
+    [C, N] holds every unit's tallied values in ascending order; a value's quantile is the
+    centre-of-interval rank the reference's RunningQuantile.normalize interpolates (ties and
+    the exact interpolation differ by less than one sample)."""
+    all_obs, all_w = torch.cat(obs_list), torch.cat(weight_list)
+    n = sorted_units.shape[1]
+    x = all_obs.t().contiguous()                                    # [C, M]
+    hi = torch.searchsorted(sorted_units, x, right=True)            # samples <= x
+    lo = torch.searchsorted(sorted_units, x, right=False)           # samples <  x
+    quant = ((hi + lo).double() / 2 / n).float()
+    # at or beyond the tallied extremes the reference's interpolation returns exactly 0 / 1
+    quant = torch.where(x >= sorted_units[:, -1:], torch.ones_like(quant), quant)
+    quant = torch.where(x <= sorted_units[:, :1], torch.zeros_like(quant), quant)
+    # quantile 1 gives -log(0) = inf, and inf * (mask weight 0) = NaN: the reference does not
+    # guard against it, NaN units sort first (a selected image is re-generated alone, so its
+    # values need not lie inside the range tallied over batches of 10 — App. B #1)
+    logscore = -torch.log(1.0 - quant).t()
+    mean_logscore = (logscore * all_w).sum(0) / all_w.sum()
+    return mean_logscore.sort(descending=True)[1][:rank]
+
+
+# ---------------------------------------------------------------------------------------
 # the insert loop
 # ---------------------------------------------------------------------------------------
 def target_forward(k, style, weight, noise_w, bias, with_noise_act=True):
