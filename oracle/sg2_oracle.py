@@ -2,7 +2,8 @@
 
 A plain torch-CPU (fp32, optionally fp64) functional restatement of what the reference
 (davidbau/rewriting) computes on the path named by BASELINE.json: the SeqStyleGAN2 forward,
-the key second moment, the ZCA / key-direction algebra, projected_conv and the insert loop.
+the key second moment, the ZCA / key-direction algebra, projected_conv, the insert loop and
+the UI-search / erase statistics (ranking_for_key, normdissect, gandissect).
 Every function cites the reference file:line it follows (paths relative to the reference
 root).  Nothing here is imported by the product (`rewriting_b200/`); only tests/,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs use it — as
@@ -11,7 +12,10 @@ the checker or the timed CPU baseline, never as a fallback.
 PINNING: `oracle/make_golden.py` runs the unmodified reference under `oracle/ref_shim.py` in
 the authoring container and asserts this restatement reproduces it (bit-exactly for the
 generator, to fp32 round-off for linalg); the resulting vectors are committed under
-tests/golden/ and re-checked by `tests/test_oracle_golden.py` on every run.  The reference's own
+tests/golden/ and re-checked by `tests/test_oracle_golden.py` on every run; the search / erase
+statistics are pinned the same way by `oracle/make_golden_search.py` /
+`tests/test_oracle_search.py`, the top-k / quantile classes by `oracle/make_golden_stats.py` /
+`tests/test_stats_golden.py`.  The reference's own
 tests hold no golden vectors for this path, so the live reference is the pin.
 
 Weights are passed as a state_dict with the reference's key names (136 entries for size 256,
