@@ -13,7 +13,3 @@ echo "bench exit $?"; tail -c 600 gpurun_out/bench.err; head -c 1500 gpurun_out/
 echo "== ncu launch list"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --no-graph > gpurun_out/ncu_bench.log 2>&1
 echo "ncu exit $?"; python tools/launch_summary.py gpurun_out/launches.csv 2>&1 | head -20
-echo "== ncu full: layer-13 blur and conv"
-B="python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline --no-graph"
-timeout 150 ncu --set full --import-source on --clock-control none -k regex:blur_up_pipe -s 5 -c 1 -f -o gpurun_out/blur_pipe2 $B > gpurun_out/ncu_blur2.log 2>&1; echo "blur $?"
-timeout 150 ncu --set full --import-source on --clock-control none -k regex:conv_tc -s 11 -c 1 -f -o gpurun_out/conv_l13_lean $B > gpurun_out/ncu_conv2.log 2>&1; echo "conv $?"
