@@ -196,3 +196,14 @@ def test_checkpoint_key_conversion_from_rosinality_names(seeded_model):
             continue
         assert torch.equal(got[k], sd[k]), k
     assert got['latents.latent_avg'].shape == (512,)
+
+
+def test_shard_range_partitions_exactly():
+    from rewriting_b200 import dist as rdist
+    for n in (0, 1, 7, 16, 50010):
+        for R in (1, 2, 3, 8):
+            spans = [rdist.shard_range(n, r, R) for r in range(R)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
