@@ -16,11 +16,12 @@ __version__ = '0.1.0'
 
 def install_aliases():
     from . import utils as _utils, rewrite as _rewrite
-    from .utils import nethook, pbar, renormalize, runningstats, tally, zdataset, stylegan2
+    from .utils import imgviz, nethook, pbar, renormalize, runningstats, tally, zdataset, stylegan2
     from .rewrite import ganrewrite
     sys.modules.setdefault('utils', _utils)
     sys.modules.setdefault('rewrite', _rewrite)
-    for name, mod in [('nethook', nethook), ('pbar', pbar), ('renormalize', renormalize),
+    for name, mod in [('imgviz', imgviz), ('nethook', nethook), ('pbar', pbar),
+                      ('renormalize', renormalize),
                       ('runningstats', runningstats), ('tally', tally), ('zdataset', zdataset),
                       ('stylegan2', stylegan2)]:
         sys.modules.setdefault('utils.' + name, mod)

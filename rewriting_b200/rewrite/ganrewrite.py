@@ -34,7 +34,7 @@ import time
 import torch
 
 from .. import _cabi, ops
-from ..utils import nethook, pbar, renormalize, tally
+from ..utils import imgviz, nethook, pbar, renormalize, tally
 from ..utils.stylegan2 import models as sg2
 
 # module-level debugging handles the reference exposes (ganrewrite.py:13-14)
@@ -612,31 +612,51 @@ class ProgressiveGanRewriter(object):
 
     # ---------------------------------------------------------------------------- rendering
     def render_object(self, target_output, obj_area=None, box=None):
+        """The object rendered alone; with `box` (t, l, b, r in value-map cells) a red frame is
+        drawn around it [ganrewrite.py:596-608]."""
         with torch.no_grad():
             imgdata = self.rendered_image(self.rendering_model(target_output))
-        if box is not None:
-            raise NotImplementedError('box overlays need the imgviz/matplotlib visualiser '
-                                      '(out of scope, SURVEY.md §2.1 row 13)')
-        return renormalize.as_image(imgdata[0])
+        if box is None:
+            return renormalize.as_image(imgdata[0])
+        t, l, b, r = box
+        lowres = torch.zeros(tuple(self.v_shape[2:]))
+        lowres[t:b, l:r] = 1
+        iv = imgviz.ImageVisualizer(imgdata.shape[2:])
+        return iv.masked_image(imgdata, activations=lowres, level=0.0, border_color=[255, 0, 0],
+                               thickness=3)
+
+    def _key_heatmap(self, z, key):
+        acts = self.context_acts(self.context_model(z))
+        return (acts * key.to(self.device)[None, :, None, None]).sum(dim=1)
 
     def render_image(self, imgnum, key=None, level=None, mask=None, **kwargs):
+        """Image `imgnum` of zds; with (`key`, `level`) the region whose key response exceeds
+        `level` is outlined, with `mask` that region [ganrewrite.py:610-625]."""
         with torch.no_grad():
             imgdata = self.rendered_image(self.rendering_model(self.target_model(
                 self.context_model(self.get_z(imgnum)))))
-        if (key is not None and level is not None) or mask is not None:
-            raise NotImplementedError('heatmap / mask overlays need the imgviz/matplotlib '
-                                      'visualiser (out of scope, SURVEY.md §2.1 row 13)')
+            if key is not None and level is not None:
+                heatmap = self._key_heatmap(self.get_z(imgnum), key)[0]
+                iv = imgviz.ImageVisualizer(imgdata.shape[2:])
+                return iv.masked_image(imgdata, heatmap, level=level, **kwargs)
+        if mask is not None:
+            iv = imgviz.ImageVisualizer(imgdata.shape[2:])
+            return iv.masked_image(imgdata, mask=mask, **kwargs)
         return renormalize.as_image(imgdata[0])
 
     def render_image_batch(self, imgnums, key=None, level=None, **kwargs):
-        if key is not None and level is not None:
-            raise NotImplementedError('heatmap overlays need the imgviz/matplotlib visualiser')
         results = []
-        for i in range(0, len(imgnums), 3):
+        for i in range(0, len(imgnums), 3):                      # reference batch size
             with torch.no_grad():
                 z = torch.cat([self.get_z(n) for n in imgnums[i:i + 3]])
                 imgs = self.rendered_image(self.rendering_model(self.target_model(
                     self.context_model(z))))
+                if key is not None and level is not None:
+                    heatmap = self._key_heatmap(z, key)
+                    iv = imgviz.ImageVisualizer(imgs.shape[2:])
+                    results.extend(iv.masked_image(im, heatmap[j], level=level, **kwargs)
+                                   for j, im in enumerate(imgs))
+                    continue
             results.extend(renormalize.as_image(im) for im in imgs)
         return results
 
