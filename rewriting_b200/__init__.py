@@ -14,7 +14,15 @@ import sys
 __version__ = '0.1.0'
 
 
-def install_aliases():
+def install_aliases(reference_root=None):
+    """Register `utils` / `rewrite` as the reference's top-level package names.
+
+    With `reference_root` (or $REWRITING_REFERENCE_ROOT) pointing at a checkout of
+    davidbau/rewriting, modules this package does not provide — the notebook UI
+    (`rewrite/rewriteapp.py`, `utils/labwidget.py`, `paintwidget.py`, `show.py`) — are looked up
+    in the checkout AFTER this package's own directories, so `from rewrite import ganrewrite,
+    rewriteapp` gives this package's rewriter and the reference's device-independent UI."""
+    import os
     from . import utils as _utils, rewrite as _rewrite
     from .utils import imgviz, nethook, pbar, renormalize, runningstats, tally, zdataset, stylegan2
     from .rewrite import ganrewrite
@@ -26,3 +34,9 @@ def install_aliases():
                       ('stylegan2', stylegan2)]:
         sys.modules.setdefault('utils.' + name, mod)
     sys.modules.setdefault('rewrite.ganrewrite', ganrewrite)
+    reference_root = reference_root or os.environ.get('REWRITING_REFERENCE_ROOT')
+    if reference_root:
+        for pkg, sub in ((_utils, 'utils'), (_rewrite, 'rewrite')):
+            extra = os.path.join(reference_root, sub)
+            if os.path.isdir(extra) and extra not in pkg.__path__:
+                pkg.__path__.append(extra)

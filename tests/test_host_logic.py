@@ -207,3 +207,35 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/rewrite'),
+                    reason='needs a checkout of the reference (authoring container only)')
+def test_install_aliases_serves_the_reference_ui_over_this_rewriter():
+    """`from rewrite import ganrewrite, rewriteapp` in a notebook: this package's rewriter and
+    overlay renderer, the reference's device-independent GanRewriteApp / widgets."""
+    import subprocess
+    import sys
+    code = '''
+import sys, types
+sys.path.insert(0, %r)
+if 'IPython' not in sys.modules:
+    try:
+        import IPython
+    except ImportError:
+        m = types.ModuleType('IPython'); d = types.ModuleType('IPython.display')
+        d.display = lambda *a, **k: None; m.display = d
+        sys.modules['IPython'] = m; sys.modules['IPython.display'] = d
+import rewriting_b200
+rewriting_b200.install_aliases('/root/reference')
+from rewrite import ganrewrite, rewriteapp
+from utils import imgviz, labwidget, runningstats
+assert ganrewrite.__file__.startswith(%r), ganrewrite.__file__
+assert imgviz.__file__.startswith(%r) and runningstats.__file__.startswith(%r)
+assert rewriteapp.__file__.startswith('/root/reference') and labwidget.__file__.startswith('/root/reference')
+assert hasattr(rewriteapp, 'GanRewriteApp') and hasattr(ganrewrite, 'SeqStyleGanRewriter')
+print('ok')
+''' % (ROOT, ROOT, ROOT, ROOT)
+    r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
