@@ -331,7 +331,6 @@ def main():
         barrier()
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         launches = launches_per_step * K          # a graph replay launches the same kernels
-        clocks = sampler.stop() if rank == 0 else None
         # per-kernel CUDA-event timing of the dominant kernel: eager replay of the same steps
         # (events cannot be read back from inside a graph), CPU running ahead of the GPU
         for i in range(2):
@@ -376,6 +375,9 @@ def main():
         s1.record()
         barrier()
         ms_e2e = max_over_ranks(s0.elapsed_time(s1))
+    # SM clocks / throttle reasons sampled over all three timed loops (device-resident, per-kernel
+    # replay, end-to-end): the first alone lasts ~0.2 s, i.e. one or two nvidia-smi polls
+    clocks = sampler.stop() if rank == 0 else None
 
     value = BATCH * K * world / (ms_dev / 1e3)
     e2e_value = BATCH * K * world / (ms_e2e / 1e3)
