@@ -14,6 +14,11 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    # a fresh checkout has no librw_b200.so yet (built artefacts are git-ignored): build it once
+    # (nvcc cross-compiles sm_100a without a GPU); an existing library is left alone
+    from rewriting_b200 import build as rw_build
+    if not os.path.exists(rw_build.LIB):
+        rw_build.build(force=True)
 
 
 def pytest_collection_modifyitems(config, items):
