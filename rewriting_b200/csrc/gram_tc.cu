@@ -214,20 +214,60 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int M, int N,
-                                       long long ldp, float* __restrict__ out, long long ldo,
-                                       int accumulate, int mirror_upper) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(M) * N) return;
-  const int m = static_cast<int>(idx / N);
-  const int n = static_cast<int>(idx % N);
-  int sm = m, sn = n;
-  if (mirror_upper && m > n) { sm = n; sn = m; }  // read the transposed (computed) entry
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s)
-    acc += partial[(static_cast<size_t>(s) * M + sm) * ldp + sn];
-  float* o = out + static_cast<size_t>(m) * ldo + n;
-  *o = accumulate ? (*o + acc) : acc;
+// out[m, n] (= | +=) sum_s partial[s][m][n], 32 x 32 tiles, float reads along n (coalesced).
+// mirror_upper: only tiles on or above the diagonal are computed; an off-diagonal tile is also
+// stored transposed through shared memory, so both the reads and the two stores are full
+// 128-byte rows (the first version read the lower triangle column-wise: 32 lines per load).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int splits, int M, int N, long long ldp,
+                       float* __restrict__ out, long long ldo, int accumulate, int mirror_upper) {
+  __shared__ float tile[32][33];
+  const int tn = blockIdx.x, tm = blockIdx.y;
+  if (mirror_upper && tm > tn) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  const size_t plane = static_cast<size_t>(M) * ldp;
+  const bool diag = mirror_upper && tm == tn;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lm = ty + r * 8;
+    const int m = tm * 32 + lm, n = tn * 32 + tx;
+    float acc = 0.f;
+    if (m < M && n < N && !(diag && lm > tx)) {
+      const float* src = partial + static_cast<size_t>(m) * ldp + n;
+      for (int s = 0; s < splits; ++s) acc += src[s * plane];
+      float* o = out + static_cast<size_t>(m) * ldo + n;
+      *o = accumulate ? (*o + acc) : acc;
+    }
+    tile[lm][tx] = acc;
+  }
+  if (!mirror_upper) return;
+  if (diag) {
+    // diagonal tile: the strictly-lower entries are the transposed upper ones (bit-identical,
+    // so the accumulated matrix stays exactly symmetric)
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int lm = ty + r * 8;
+      const int m = tm * 32 + lm, n = tn * 32 + tx;
+      if (lm > tx && m < M && n < N) {
+        const float v = tile[tx][lm];
+        float* o = out + static_cast<size_t>(m) * ldo + n;
+        *o = accumulate ? (*o + v) : v;
+      }
+    }
+    return;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ln = ty + r * 8;                  // row of the mirrored tile = column of this one
+    const int m2 = tn * 32 + ln, n2 = tm * 32 + tx;
+    if (m2 < N && n2 < M) {
+      float* o = out + static_cast<size_t>(m2) * ldo + n2;
+      const float v = tile[tx][ln];
+      *o = accumulate ? (*o + v) : v;
+    }
+  }
 }
 
 }  // namespace
@@ -284,11 +324,9 @@ int gram_tc_launch(const GramTcParams& p, const void* a_hi, const void* a_lo, co
 int reduce_partials_launch(const float* partial, int splits, int M, int N, long long ldp,
                            float* out, long long ldo, int accumulate, int mirror_upper,
                            cudaStream_t stream) {
-  const long long total = static_cast<long long>(M) * N;
-  const int threads = 256;
-  const int blocks = static_cast<int>((total + threads - 1) / threads);
-  reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial, splits, M, N, ldp, out, ldo,
-                                                         accumulate, mirror_upper);
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  reduce_partials_kernel<<<grid, 256, 0, stream>>>(partial, splits, M, N, ldp, out, ldo, accumulate,
+                                                   mirror_upper);
   return check_cuda(cudaGetLastError(), "reduce_partials launch");
 }
 

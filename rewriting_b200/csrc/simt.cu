@@ -846,14 +846,16 @@ struct StyleJobs {
 // row, so the kernel is not a chain of dependent weight loads (measured: 24 us -> a few us per
 // mapping layer).
 __global__ void __launch_bounds__(256)
-styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, float scale,
-              float bias_mul, int act, int cpw, const StyleJobs jobs) {
-  extern __shared__ float xs[];            // [B][K]
+styles_kernel(const float* __restrict__ latent, int Btotal, int bchunk, int n_latent, int K,
+              float scale, float bias_mul, int act, int cpw, const StyleJobs jobs) {
+  extern __shared__ float xs[];            // [B][K], B = this block's batch chunk (blockIdx.y)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int l = 0;
   const int blk = blockIdx.x;
   while (blk >= jobs.first_warp[l + 1]) ++l;          // first_warp holds BLOCK offsets here
-  const float* x0 = latent + static_cast<size_t>(jobs.lat[l]) * K;
+  const int b_begin = blockIdx.y * bchunk;
+  const int B = min(bchunk, Btotal - b_begin);
+  const float* x0 = latent + (static_cast<size_t>(b_begin) * n_latent + jobs.lat[l]) * K;
   if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(x0) & 15u) == 0) {
     const int kq = K >> 2;
     float4* xs4 = reinterpret_cast<float4*>(xs);
@@ -869,7 +871,7 @@ styles_kernel(const float* __restrict__ latent, int B, int n_latent, int K, floa
   }
   __syncthreads();
   const int C = jobs.chans[l];
-  float* out = jobs.out[l];
+  float* out = jobs.out[l] + static_cast<size_t>(b_begin) * C;
   const int nk = (K + 31) >> 5;
   for (int cc = 0; cc < cpw; ++cc) {
     const int c = ((blk - jobs.first_warp[l]) * 8 + warp) * cpw + cc;
@@ -1249,9 +1251,15 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     warps += (chans[i] + 8 * cpw - 1) / (8 * cpw);          // blocks of 8*cpw channels
   }
   jobs.first_warp[n] = warps;
-  const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
+  // the latent rows of a block are staged in shared memory, and that staging (not the FMAs) is
+  // what a block spends its time on: 16-row chunks over blockIdx.y keep it at 32 KB per block
+  // (8 blocks per SM) whatever the batch size; the weight rows are re-read from L2 per chunk
+  int bchunk = B < 16 ? B : 16;
+  while (static_cast<size_t>(bchunk) * K * sizeof(float) > 128 * 1024 && bchunk > 1)
+    bchunk = (bchunk + 1) / 2;
+  const size_t smem = static_cast<size_t>(bchunk) * K * sizeof(float);
   if (smem > 200 * 1024) {
-    set_last_error("styles: B*K too large for shared memory");
+    set_last_error("styles: K too large for shared memory");
     return RW_ERR_UNSUPPORTED;
   }
   static size_t attr = 0;
@@ -1262,8 +1270,9 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
     if (rc) return rc;
     attr = smem;
   }
-  styles_kernel<<<warps, 256, smem, stream>>>(latent, B, n_latent, K, scale, bias_mul, act, cpw,
-                                              jobs);
+  dim3 grid(warps, (B + bchunk - 1) / bchunk);
+  styles_kernel<<<grid, 256, smem, stream>>>(latent, B, bchunk, n_latent, K, scale, bias_mul, act,
+                                             cpw, jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
 }
 

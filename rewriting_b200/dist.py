@@ -60,7 +60,7 @@ def sharded_second_moment(compute, dataset, sample_size=None, batch_size=10, cac
     cached = tally.load_cached_state(cachefile, args)
     if cached is not None:
         return runningstats.RunningSecondMoment(state=cached)
-    loader = tally.make_loader(dataset, sample_size, batch_size)
+    loader = tally.batches(dataset, sample_size, batch_size)
     r2mom = runningstats.RunningSecondMoment()
     R, r = world_size(), rank()
     for j, batch in enumerate(pbar(loader)):

@@ -123,9 +123,14 @@ def forward(model, z, upto_key_layer=None):
     K = w_lat.shape[1]
     run = [l for l in layers if upto_key_layer is None or l[0] < upto_key_layer]
     if upto_key_layer is not None:
-        # key collection: the running RGB image feeds nothing, skip every ToRGB
-        layers = [(num, sconv, lat, None, None) for num, sconv, lat, _, _ in layers]
+        # key collection: the running RGB image feeds nothing, skip every ToRGB; layers past the
+        # key layer are never run, so neither their styles nor their demodulation factors are
+        # computed (the key layer's own style scales the last producer's output planes)
+        layers = [(num, sconv, lat, None, None) for num, sconv, lat, _, _ in layers
+                  if num <= upto_key_layer]
         run = [(num, sconv, lat, None, None) for num, sconv, lat, _, _ in run]
+        if not layers or layers[-1][0] != upto_key_layer:
+            raise ValueError('layer%s not found' % upto_key_layer)
 
     # all styles up front (they only depend on the latent): ONE launch for the 13 + 7
     # modulation linears instead of 20 tiny sgemms

@@ -132,24 +132,42 @@ class ProgressiveGanRewriter(object):
         return [p for n, p in self.target_model.named_parameters() if 'weight' in n][0]
 
     # ---------------------------------------------------------------------------- statistics
+    # z per context pass of the covariance collection.  The reference tallies batches of 10
+    # (tally.py:424-443); C is a plain sum over samples, so the batch size only changes the fp32
+    # summation order (C rel-Frobenius ~1e-7).  The fused key capture is launch- and tail-bound
+    # below a few hundred z per pass (the 4x4..16x16 convs are a handful of tiles each).
+    FAST_MOMENT_BATCH = 256
+
+    def _fast_key_layer(self):
+        """N if the keys are the operand planes of `layerN...dconv` of an intact SeqStyleGAN2
+        (then the fused generation pipeline, stopped in front of that conv, produces them)."""
+        m = _DCONV_RE.match(self.firstlayer)
+        if m and isinstance(self.model, sg2.SeqStyleGAN2) and self.model.mconv == 'seq' and \
+                not self.model.bag_input and not sg2._is_hooked(self.model):
+            from .. import fastpath
+            if fastpath._layer_list(self.model) is not None:
+                return int(m.group(1))
+        return None
+
     def _key_planes(self, zbatch):
         """context forward -> bf16 hi/lo planes of the keys (rows = pixels, cols = channels).
         When the key is the input of `layerN...dconv` of an intact SeqStyleGAN2, the fused
         generation pipeline is run up to that convolution and its operand planes ARE the keys
         (no fp32 key tensor, no permute)."""
         from .. import fastpath
-        z = zbatch.to(self.device)
-        m = _DCONV_RE.match(self.firstlayer)
-        if m and isinstance(self.model, sg2.SeqStyleGAN2) and fastpath.eligible(self.model, z):
-            return self._graphed_key_planes(z, int(m.group(1)))
+        z = zbatch.to(self.device, non_blocking=True)
+        layer = self._fast_key_layer()
+        if layer is not None and fastpath.eligible(self.model, z):
+            if z.shape[0] == getattr(self, '_moment_bs', None):
+                return self._graphed_key_planes(z, layer)
+            return fastpath.forward(self.model, z, upto_key_layer=layer)   # ragged last batch
         acts = self.context_acts(self.context_model(z))
         planes, _ = ops.prep_keys(acts, None)
         return planes
 
     def _graphed_key_planes(self, z, layer):
-        """The context pass for one z batch is ~40 short kernels (launch-bound at the reference's
-        batch size of 10), so it is captured once per batch shape into a CUDA graph and replayed;
-        the capture is redone if any parameter changed since (edits bump `_version`)."""
+        """The context pass is ~40 kernels; captured once per batch shape into a CUDA graph and
+        replayed; the capture is redone if any parameter changed since (edits bump `_version`)."""
         from .. import fastpath
         from ..graphs import GraphedModule
         versions = tuple(p._version for p in self.model.parameters())
@@ -163,18 +181,27 @@ class ProgressiveGanRewriter(object):
             cache[key] = ent
         return ent[1](z)
 
-    def collect_2nd_moment(self):
+    def collect_2nd_moment(self, batch_size=None):
         """C = E[k k^T] (uncentered), computed or loaded from `r2m.npz` [ganrewrite.py:83-96].
         On >1 ranks (torch.distributed initialised) the z batches are sharded and mom2/count
         all-reduced; every rank returns the same matrix and rank 0 writes the cache."""
         from .. import dist as rdist
+        R = rdist.world_size()
+        if batch_size is None:
+            batch_size = 10
+            if self._fast_key_layer() is not None:
+                per_rank = -(-len(self.zds) // R)
+                batch_size = max(1, min(self.FAST_MOMENT_BATCH, per_rank))
+        self._moment_bs = batch_size
         with torch.no_grad(), pbar.quiet():
-            if rdist.world_size() > 1:
+            if R > 1:
                 r2m = rdist.sharded_second_moment(self._key_planes, self.zds,
+                                                  batch_size=batch_size,
                                                   cachefile=self.rf('r2m.npz'),
                                                   device=self.device)
             else:
                 r2m = tally.tally_second_moment(self._key_planes, self.zds,
+                                                batch_size=batch_size,
                                                 cachefile=self.rf('r2m.npz'))
             return r2m.moment()
 

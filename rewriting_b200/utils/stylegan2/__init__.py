@@ -50,7 +50,9 @@ def load_state_dict(category, path=None):
 
 
 def load_seq_stylegan(category, truncation=1.0, path=None, **kwargs):
-    """The nn.Sequential StyleGAN2 for `category`, weights loaded, on the GPU."""
+    """The nn.Sequential StyleGAN2 for `category`, weights loaded, on the GPU.
+    `real_truncation=True` (keyword, not in the reference) makes `truncation` really apply;
+    the default reproduces the reference, whose 0-dim `latent_avg` buffer silently disables it."""
     ckpt = load_state_dict(category, path=path)
     net = SeqStyleGAN2(sizes[category], style_dim=512, n_mlp=8, truncation=truncation, **kwargs)
     net.load_state_dict(ckpt['g_ema'], latent_avg=ckpt['latent_avg'])

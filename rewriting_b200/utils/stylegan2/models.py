@@ -504,8 +504,14 @@ class SeqStyleGAN2(nn.Sequential):
     """
 
     def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1],
-                 lr_mlp=0.01, truncation=1.0, mconv=None, bag_input=False, bag_output=False):
+                 lr_mlp=0.01, truncation=1.0, mconv=None, bag_input=False, bag_output=False,
+                 real_truncation=False):
         self.size = size
+        # False (default) = the reference's behaviour: `latent_avg` stays a 0-dim buffer, so
+        # AdjustLatent never truncates whatever `truncation` says and
+        # images for a given z / imgnum are the reference's.  True = size the buffer from the
+        # checkpoint and really truncate (a deviation).
+        self.real_truncation = real_truncation
         self.style_dim = style_dim
         self.mconv = mconv
         self.bag_input = bag_input
@@ -607,9 +613,15 @@ class SeqStyleGAN2(nn.Sequential):
         if latent_avg is not None:
             latent_avg = torch.as_tensor(latent_avg)
             if latent_avg.ndim > 0 and self.latents.latent_avg.ndim == 0:
-                # size the buffer from the checkpoint so that truncation really applies
-                self.latents.latent_avg = torch.zeros_like(
-                    latent_avg, device=self.latents.latent_avg.device)
+                if self.real_truncation:
+                    # opt-in: size the buffer from the checkpoint so that truncation applies
+                    self.latents.latent_avg = torch.zeros_like(
+                        latent_avg, device=self.latents.latent_avg.device)
+                else:
+                    # the reference's torch (1.x) loaded a 1-D tensor into the 0-dim buffer as
+                    # its first element (the 0.3->0.4 back-compat rule), leaving it 0-dim:
+                    # AdjustLatent.forward then skips truncation (models.py:577-582)
+                    latent_avg = latent_avg.reshape(-1)[0].clone()
             converted['latents.latent_avg'] = latent_avg
         elif 'latents.latent_avg' not in converted:
             if self.latents.truncation != 1.0:

@@ -43,6 +43,24 @@ def make_loader(dataset, sample_size=None, batch_size=10, sampler=None, **kwargs
     return torch.utils.data.DataLoader(dataset, sampler=sampler, batch_size=batch_size, **kwargs)
 
 
+def batches(dataset, sample_size=None, batch_size=10, **kwargs):
+    """What iterating `make_loader(...)` yields, without the DataLoader when the dataset is a
+    plain tensor / TensorDataset read in order: slices of the tensors (one list per batch, like
+    the default collate).  At batch sizes in the hundreds the per-item collate of a DataLoader
+    (one Python call per row) costs more than the GPU work of the batch."""
+    if isinstance(dataset, torch.Tensor):
+        dataset = torch.utils.data.TensorDataset(dataset)
+    if kwargs or type(dataset) is not torch.utils.data.TensorDataset:
+        return make_loader(dataset, sample_size, batch_size, **kwargs)
+    n = len(dataset)
+    if sample_size is not None:
+        if sample_size > n:
+            pbar.print('Warning: sample size %d > dataset size %d' % (sample_size, n))
+        n = min(n, sample_size)
+    tensors = dataset.tensors
+    return [[t[i:min(i + batch_size, n)] for t in tensors] for i in range(0, n, batch_size)]
+
+
 def load_cached_state(cachefile, args):
     if cachefile is None:
         return None
@@ -79,7 +97,7 @@ def tally_second_moment(compute, dataset, sample_size=None, batch_size=10, cache
     cached = load_cached_state(cachefile, args)
     if cached is not None:
         return runningstats.RunningSecondMoment(state=cached)
-    loader = make_loader(dataset, sample_size, batch_size, **kwargs)
+    loader = batches(dataset, sample_size, batch_size, **kwargs)
     r2mom = runningstats.RunningSecondMoment()
     for batch in pbar(loader):
         sample = call_compute(compute, batch)

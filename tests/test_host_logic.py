@@ -195,7 +195,18 @@ def test_checkpoint_key_conversion_from_rosinality_names(seeded_model):
         if k == 'latents.latent_avg' or k.startswith('noises'):
             continue
         assert torch.equal(got[k], sd[k]), k
-    assert got['latents.latent_avg'].shape == (512,)
+    # reference-compatible default: the buffer stays 0-dim (no truncation, same images as the
+    # reference for a given z); real_truncation=True is the explicit opt-in
+    assert got['latents.latent_avg'].ndim == 0
+    opt = sg2.SeqStyleGAN2(256, 512, 8, mconv='seq', truncation=0.5, real_truncation=True)
+    opt.load_state_dict({'g_ema': ros, 'latent_avg': torch.arange(512.)})
+    assert opt.state_dict()['latents.latent_avg'].shape == (512,)
+    w = torch.randn(3, 512)
+    lat = opt.latents(sg2.DataBag(latent=w)).latent
+    assert torch.allclose(lat[:, 0], torch.arange(512.) + 0.5 * (w - torch.arange(512.)))
+    keep = sg2.SeqStyleGAN2(256, 512, 8, mconv='seq', truncation=0.5)
+    keep.load_state_dict({'g_ema': ros, 'latent_avg': torch.arange(512.)})
+    assert torch.equal(keep.latents(sg2.DataBag(latent=w)).latent[:, 0], w)
 
 
 def test_shard_range_partitions_exactly():

@@ -55,6 +55,6 @@ template <int N> void run(int grid) {
   cudaFree(d);
 }
 int main() {
-  for (int grid : {1, 148}) { run<64>(grid); run<128>(grid); run<256>(grid); }
+  for (int grid : {1, 148}) { run<64>(grid); run<128>(grid); run<144>(grid); run<160>(grid); run<192>(grid); run<224>(grid); run<256>(grid); }
   return 0;
 }
