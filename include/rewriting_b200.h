@@ -109,6 +109,19 @@ int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const fl
                      const float* noise, long long noise_bstride, const float* noise_w,
                      const float* bias, int act, const float* next_scale, void* next_hi,
                      void* next_lo, float* y_out, rw_stream_t stream);
+/* The whole upsampling StyledConv of the fast path in ONE kernel (csrc/upconv_tc.cu):
+ * conv_transpose2d(stride 2) -> 4x4 blur (pad 1,1) -> * demod -> + noise_w*noise + bias ->
+ * leaky-ReLU*sqrt(2) -> * next_scale -> the next layer's bf16 hi/lo planes (pad row/column zeroed).
+ * Replaces the reference chain models.py:313-329 (DemodulatedConv2dF, upsample branch) -> :275-281
+ * (BlurF / upfirdn2d_kernel.cu:52-137) -> :535-546 (NoiseInjectionF) -> fused_bias_act_kernel.cu
+ * :27-47, without ever writing the (2H+1)x(2W+1) fp32 conv_transpose output.
+ * wt_{hi,lo}: rw_prep_weights(transpose_io = 2) planes [Cout/16][9][16][Cin].  W must be a power
+ * of two in [4, 128], Cin % 64 == 0, Cout % 16 == 0, the 4x4 kernel rank one (separable). */
+int rw_modconv_up_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                        const float* demod, const float* kernel4x4, const float* noise,
+                        long long noise_bstride, const float* noise_w, const float* bias,
+                        const float* next_scale, void* next_hi, void* next_lo, int B, int Cin,
+                        int Cout, int H, int W, rw_stream_t stream);
 /* all modulation linears in one launch: out_l[b,c] = latent[b,lat_l,:] . (W_l[c,:]*scale) + bias_l[c]
  * (HOST arrays of n device pointers / ints; n <= 32) */
 int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int n,
@@ -131,6 +144,12 @@ int rw_demod_multi(int B, float eps, int n, const float* const* style, const flo
                    const float* wscale, rw_stream_t stream);
 int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const float* bias,
                    const float* prev, const float* kernel4x4, float* out, rw_stream_t stream);
+/* same, and/or the image as NHWC bytes  clamp(x*127.5 + 127.5, 0, 255)  (uint8 truncation): the
+ * output side of the sampling loops (metrics/sample.py:33-37, utils/get_samples.py:121-127 move
+ * fp32 NCHW images to the host one by one); `out` may be NULL when only the bytes are wanted */
+int rw_rgb_combine_u8(const float* part, int nparts, int B, int H, int W, const float* bias,
+                      const float* prev, const float* kernel4x4, float* out,
+                      unsigned char* out_u8_nhwc, rw_stream_t stream);
 /* y = act( upfirdn2d(t, k4x4, pad=(1,1)) + noise_w*noise + bias ), t [B,C,2H+1,2W+1] -> y [B,C,2H,2W] */
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
                    const float* noise, long long noise_bstride, const float* noise_w,
@@ -225,10 +244,25 @@ typedef struct rw_insert_args {
   int rank, B, Cin, Cout, h, w;
   int has_noise_act;      /* 1: target = dconv->noise->activate, 0: dconv only */
   int it0, nsteps, niter_total, piter, project_gradient;
+  /* appended in round 2 (zero = the StyleGAN2 behaviour of round 1): */
+  int plain_conv;          /* 1: y = conv(k, W) with no style demodulation and no 1/sqrt(9 Cin)
+                              weight scale — the `layerN.conv` target of ProgressiveGanRewriter
+                              (ganrewrite.py:25-96; `style` is then ignored and may be NULL) */
+  float one_minus_beta1;   /* torch.optim.Adam forms 1-beta in double and rounds once to float */
+  float one_minus_beta2;   /* (0 -> computed in the kernel as 1.0f - beta) */
+  double beta1_exact;      /* the betas as the Python doubles torch forms its bias corrections */
+  double beta2_exact;      /* 1 - beta**step from (0 -> the float fields above, widened) */
 } rw_insert_args;
 int rw_insert_loop(const rw_insert_args* args, rw_stream_t stream);
 
 /* ---- bring-up hooks (tests/tools only) ---- */
+/* rw_modconv_up_fused with demod = next_scale = ones_bo, additionally dumping the raw tap products
+ * P[b][y][x][tap][Cout] of the tensor-core stage */
+int rw_debug_upconv_taps(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                         const float* ones_bo, const float* kernel4x4, const float* noise,
+                         long long noise_bstride, const float* noise_w, const float* bias,
+                         void* next_hi, void* next_lo, int B, int Cin, int Cout, int H, int W,
+                         float* taps_out, rw_stream_t stream);
 int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                      int rows, int K, int N, float* out, rw_stream_t stream);
 int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,

@@ -32,6 +32,8 @@ class InsertArgs(ctypes.Structure):
         ('h', c_int), ('w', c_int), ('has_noise_act', c_int),
         ('it0', c_int), ('nsteps', c_int), ('niter_total', c_int),
         ('piter', c_int), ('project_gradient', c_int),
+        ('plain_conv', c_int), ('one_minus_beta1', c_f), ('one_minus_beta2', c_f),
+        ('beta1_exact', ctypes.c_double), ('beta2_exact', ctypes.c_double),
     ]
 
 
@@ -54,6 +56,10 @@ SIGNATURES = {
                                      c_p, c_p, c_p]),
     'rw_modconv_up_fwd_cl': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
                                      c_p, c_p]),
+    'rw_modconv_up_fused': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p,
+                                    c_int, c_int, c_int, c_int, c_int, c_p]),
+    'rw_debug_upconv_taps': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p,
+                                     c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     'rw_blur_up_fused': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                  c_int, c_p, c_p, c_p, c_p, c_p]),
     'rw_styles': (c_int, [c_p, c_int, c_int, c_int, c_f, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -61,6 +67,7 @@ SIGNATURES = {
     'rw_pixel_norm': (c_int, [c_p, c_int, c_int, c_p, c_p]),
     'rw_demod_multi': (c_int, [c_int, c_f, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     'rw_rgb_combine': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
+    'rw_rgb_combine_u8': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     'rw_blur_up_act': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                c_int, c_p, c_p]),
     'rw_add_noise': (c_int, [c_p, c_p, c_ll, c_p, c_int, c_int, c_int, c_p, c_p]),

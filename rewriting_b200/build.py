@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'librw_b200.so')
-SOURCES = ['api.cu', 'conv_tc.cu', 'gram_tc.cu', 'simt.cu', 'bwd.cu', 'rewrite.cu']
+SOURCES = ['api.cu', 'conv_tc.cu', 'upconv_tc.cu', 'gram_tc.cu', 'simt.cu', 'bwd.cu', 'rewrite.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo', '-O3', '-std=c++17',

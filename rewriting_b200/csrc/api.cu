@@ -84,6 +84,34 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return RW_OK;
 }
 
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4],
+                      const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return RW_ERR_NO_DRIVER_SYMBOL;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 0xF) != 0) {
+    set_last_error("TMA operand must be 16-byte aligned (ptr=%p)", base);
+    return RW_ERR_BAD_ARG;
+  }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4d) failed: CUresult %d (dims %llu %llu %llu %llu box %u %u "
+                   "%u %u)", (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1], box[2],
+                   box[3]);
+    return RW_ERR_CUDA;
+  }
+  return RW_OK;
+}
+
 // split heuristic shared by the workspace query and the launches
 static int gram_splits(int tiles, long long rows, int ntaps) {
   const long long total_rb = (rows + 63) / 64;
@@ -318,6 +346,40 @@ int rw_modconv_fwd_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi
   return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
 }
 
+int rw_modconv_up_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                        const float* demod, const float* kernel4x4, const float* noise,
+                        long long noise_bstride, const float* noise_w, const float* bias,
+                        const float* next_scale, void* next_hi, void* next_lo, int B, int Cin,
+                        int Cout, int H, int W, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !demod || !kernel4x4 || !noise || !noise_w || !bias ||
+      !next_scale || !next_hi || !next_lo || (noise_bstride & 1)) {
+    set_last_error("rw_modconv_up_fused: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  UpFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W;
+  p.demod = demod; p.bias = bias; p.noise = noise; p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w; p.k4 = kernel4x4; p.next_scale = next_scale;
+  p.next_hi = next_hi; p.next_lo = next_lo;
+  return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
+}
+
+int rw_debug_upconv_taps(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                         const float* ones_bo, const float* kernel4x4, const float* noise,
+                         long long noise_bstride, const float* noise_w, const float* bias,
+                         void* next_hi, void* next_lo, int B, int Cin, int Cout, int H, int W,
+                         float* taps_out, rw_stream_t stream) {
+  UpFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W;
+  p.demod = ones_bo; p.bias = bias; p.noise = noise; p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w; p.k4 = kernel4x4; p.next_scale = ones_bo;
+  p.next_hi = next_hi; p.next_lo = next_lo;
+  p.debug_p = taps_out;
+  return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
+}
+
 int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const float* kernel4x4,
                      const float* noise, long long noise_bstride, const float* noise_w,
                      const float* bias, int act, const float* next_scale, void* next_hi,
@@ -375,7 +437,17 @@ int rw_rgb_combine(const float* part, int nparts, int B, int H, int W, const flo
     set_last_error("rw_rgb_combine: bad argument");
     return RW_ERR_BAD_ARG;
   }
-  return rgb_combine_launch(part, nparts, B, H, W, bias, prev, kernel4x4, out, stream);
+  return rgb_combine_launch(part, nparts, B, H, W, bias, prev, kernel4x4, out, nullptr, stream);
+}
+
+int rw_rgb_combine_u8(const float* part, int nparts, int B, int H, int W, const float* bias,
+                      const float* prev, const float* kernel4x4, float* out,
+                      unsigned char* out_u8_nhwc, rw_stream_t stream) {
+  if (!part || nparts < 1 || !bias || (!out && !out_u8_nhwc) || (prev && !kernel4x4)) {
+    set_last_error("rw_rgb_combine_u8: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return rgb_combine_launch(part, nparts, B, H, W, bias, prev, kernel4x4, out, out_u8_nhwc, stream);
 }
 
 int rw_blur_up_act(const float* t, int B, int C, int Hin, int Win, const float* kernel4x4,
@@ -639,8 +711,8 @@ int rw_project_rank(const float* w, const float* base, const float* d, int rank,
 }
 
 int rw_insert_loop(const rw_insert_args* a, rw_stream_t stream) {
-  if (!a || !a->W || !a->m || !a->v || !a->d || !a->key_cl || !a->style || !a->target ||
-      !a->loss_out || (a->has_noise_act && !a->bias)) {
+  if (!a || !a->W || !a->m || !a->v || !a->d || !a->key_cl || (!a->style && !a->plain_conv) ||
+      !a->target || !a->loss_out || (a->has_noise_act && !a->bias)) {
     set_last_error("rw_insert_loop: bad argument");
     return RW_ERR_BAD_ARG;
   }
@@ -656,6 +728,11 @@ int rw_insert_loop(const rw_insert_args* a, rw_stream_t stream) {
   p.piter = a->piter > 0 ? a->piter : 1;
   p.project_gradient = a->project_gradient;
   p.loss_out = a->loss_out;
+  p.plain_conv = a->plain_conv;
+  p.one_minus_beta1 = a->one_minus_beta1 != 0.f ? a->one_minus_beta1 : 1.0f - a->beta1;
+  p.one_minus_beta2 = a->one_minus_beta2 != 0.f ? a->one_minus_beta2 : 1.0f - a->beta2;
+  p.beta1_exact = a->beta1_exact != 0.0 ? a->beta1_exact : static_cast<double>(a->beta1);
+  p.beta2_exact = a->beta2_exact != 0.0 ? a->beta2_exact : static_cast<double>(a->beta2);
   return insert_loop_launch(p, stream);
 }
 

@@ -92,7 +92,8 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
   float* GS = misc + 64;               // [kWarps][OC][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float sc = rsqrtf(static_cast<float>(Cin * 9));
+  const bool plain = p.plain_conv != 0;  // nn.Conv2d target: no demodulation, no weight scale
+  const float sc = plain ? 1.0f : rsqrtf(static_cast<float>(Cin * 9));
   const int nch = Cin / 32;            // channels per lane
   const float inv_numel = 1.0f / static_cast<float>(static_cast<long long>(B) * p.Cout * h * w);
 
@@ -109,6 +110,10 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
       // ---- demod[oc][b] = rsqrt(sum_i style^2 * sum_uv (sc W)^2 + 1e-8): warp <-> (oc, b)
       for (int ob = warp; ob < OC * B; ob += kWarps) {
         const int oc = ob / B, b = ob - oc * B;
+        if (plain) {
+          if (lane == 0) demodS[oc * 4 + b] = 1.0f;
+          continue;
+        }
         float acc = 0.f;
         for (int j = 0; j < nch; ++j) {
           const int i = lane + 32 * j;
@@ -234,18 +239,18 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
         float G = 0.f;
         for (int wv = 0; wv < kWarps; ++wv) G += GS[(wv * OC + oc) * 4 + bb];
         const float dm = demodS[oc * 4 + bb];
-        coefS[oc * 4 + bb] = (bb < B) ? G * dm * dm * dm : 0.f;
+        coefS[oc * 4 + bb] = (bb < B && !plain) ? G * dm * dm * dm : 0.f;
       }
       __syncthreads();
 
       // Adam bias corrections as torch.optim.Adam computes them (python doubles)
       const double stepd = static_cast<double>(it + 1);
-      const double bc1 = 1.0 - pow(static_cast<double>(p.beta1), stepd);
-      const double bc2 = 1.0 - pow(static_cast<double>(p.beta2), stepd);
+      const double bc1 = 1.0 - pow(p.beta1_exact, stepd);
+      const double bc2 = 1.0 - pow(p.beta2_exact, stepd);
       const float step_size = static_cast<float>(static_cast<double>(p.lr) / bc1);
       const float bc2_sqrt = static_cast<float>(sqrt(bc2));
-      const float one_m_b1 = 1.0f - p.beta1;
-      const float one_m_b2 = 1.0f - p.beta2;
+      const float one_m_b1 = p.one_minus_beta1;
+      const float one_m_b2 = p.one_minus_beta2;
 
       // ---- weight gradient: warp <-> channel group j, lane <-> input channel; OC x 9 accumulators
       for (int j = warp; j < nch; j += kWarps) {
@@ -284,9 +289,11 @@ insert_loop_kernel(const InsertLoopParams p, const float* __restrict__ kpT) {
 #pragma unroll
         for (int oc = 0; oc < OC; ++oc) {
           float cs = 0.f;
-          for (int b = 0; b < B; ++b) {
-            const float s = __ldg(p.style + b * Cin + i);
-            cs = fmaf(coefS[oc * 4 + b], s * s, cs);
+          if (!plain) {
+            for (int b = 0; b < B; ++b) {
+              const float s = __ldg(p.style + b * Cin + i);
+              cs = fmaf(coefS[oc * 4 + b], s * s, cs);
+            }
           }
 #pragma unroll
           for (int t = 0; t < 9; ++t) {

@@ -55,6 +55,28 @@ int conv_tc_launch(const ConvTcParams& p, const void* a_hi, const void* a_lo, co
                    const void* w_lo, int wk_total, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
+// fused upsampling StyledConv (upconv_tc.cu): conv_transpose + blur + demod + noise + bias +
+// leaky-ReLU + next-layer style -> bf16 hi/lo planes, one kernel, no fp32 intermediate
+// ---------------------------------------------------------------------------
+struct UpFusedParams {
+  int B, Cin, Cout, H, W;      // input resolution H x W (W a power of two, 4..128)
+  const float* demod;          // [B, Cout]
+  const float* bias;           // [Cout]
+  const float* noise;          // [B, noise_bstride], indexed Y * 2W + X at OUTPUT resolution
+  long long noise_bstride;
+  const float* noise_w;        // device scalar
+  const float* k4;             // 4x4 blur kernel (rank one)
+  const float* next_scale;     // [B, Cout] style of the consuming layer
+  void* next_hi;               // [B][2H+1][2W+1][Cout] bf16 planes (pad row / column zeroed)
+  void* next_lo;
+  int ncg, nbands, nitems;     // filled by the launcher
+  float* debug_p;              // bring-up: raw tap products P[b][y][x][tap][Cout] (y < H), or null
+};
+// weights: bf16 hi/lo planes [Cout/16][9 taps][16][Cin]  (rw_prep_weights, transpose_io = 2)
+int upconv_fused_launch(const UpFusedParams& p, const void* a_hi, const void* a_lo,
+                        const void* w_hi, const void* w_lo, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
 // col-GEMM (gram_tc.cu):  out[m, n] = sum_r A[r + shift_a, m] * B[r + shift_b, n]
 // ---------------------------------------------------------------------------
 struct GramTcParams {
@@ -103,7 +125,8 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
                          const float* bias, int act, const float* next_scale, void* next_hi,
                          void* next_lo, float* y_out, cudaStream_t stream);
 int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
-                       const float* prev, const float* k4, float* out, cudaStream_t stream);
+                       const float* prev, const float* k4, float* out, unsigned char* out_u8,
+                       cudaStream_t stream);
 int styles_launch(const float* latent, int B, int n_latent, int K, float scale, float bias_mul,
                   int act, int n, const float* const* w, const float* const* bias,
                   float* const* out, const int* lat, const int* chans, cudaStream_t stream);
@@ -166,6 +189,9 @@ struct InsertLoopParams {
   int piter;
   int project_gradient; // low_rank_gradient
   float* loss_out;      // [nsteps, Cout] per-channel partial |v*-y| sums
+  int plain_conv;       // 1: no demodulation, weight scale 1 (ProgGAN `layerN.conv`)
+  float one_minus_beta1, one_minus_beta2;   // 1-beta as torch forms it (double, rounded once)
+  double beta1_exact, beta2_exact;          // betas for the bias corrections (python doubles)
 };
 int insert_loop_launch(const InsertLoopParams& p, cudaStream_t stream);
 

@@ -149,6 +149,7 @@ __global__ void split_rows_kernel(const float* __restrict__ a, long long n,
 // prep_weights: W[Cout][Cin][3][3] fp32 -> (scale*W) as bf16 hi/lo planes
 //   transpose_io = 0: Wt[o][tap][i]            (forward conv / conv_transpose)
 //   transpose_io = 1: Wt[i][tap'][o]           (dgrad), tap' = 8 - tap if flip
+//   transpose_io = 2: Wt[o/16][tap][o%16][i]   (fused upsampling conv, upconv_tc.cu)
 // and wsq[o][i] = sum_taps (scale*W)^2   (for demod, models.py:325-327)
 // one thread per (o, i)
 // ---------------------------------------------------------------------------
@@ -170,6 +171,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, int Cout, int C
     size_t dst;
     if (!transpose_io) {
       dst = (static_cast<size_t>(o) * 9 + tap) * Cin + i;
+    } else if (transpose_io == 2) {     // [Cout/16][tap][16][Cin]: the fused up-conv's N = 144 tiles
+      dst = ((static_cast<size_t>(o >> 4) * 9 + tap) * 16 + (o & 15)) * Cin + i;
     } else {
       const int tp = flip_taps ? 8 - tap : tap;
       dst = (static_cast<size_t>(i) * 9 + tp) * Cout + o;
@@ -778,7 +781,8 @@ blur_up_pipe_kernel(const float* __restrict__ t_cl, int B, int C, int H, int W,
 __global__ void __launch_bounds__(256)
 rgb_combine_kernel(const float* __restrict__ part, int nparts, long long part_stride, int H, int W,
                    const float* __restrict__ bias, const float* __restrict__ prev,
-                   const float* __restrict__ k4, float* __restrict__ out) {
+                   const float* __restrict__ k4, float* __restrict__ out,
+                   uint8_t* __restrict__ out_u8) {
   const int xq = blockIdx.x * blockDim.x + threadIdx.x;          // quad index along x
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int bc = blockIdx.z;
@@ -820,7 +824,19 @@ rgb_combine_kernel(const float* __restrict__ part, int nparts, long long part_st
     }
     acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
   }
-  *reinterpret_cast<float4*>(out + row) = acc;
+  if (out) *reinterpret_cast<float4*>(out + row) = acc;
+  if (out_u8) {
+    // NHWC bytes of the final image: clamp(x * 127.5 + 127.5, 0, 255) truncated, i.e. exactly
+    // (img * 127.5 + 127.5).clamp(0, 255).byte() (separate multiply and add: no fma contraction)
+    const int b = bc / 3, c = bc - 3 * b;
+    uint8_t* dst = out_u8 + ((static_cast<size_t>(b) * H + y) * W + x0) * 3 + c;
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float s = fminf(fmaxf(__fadd_rn(__fmul_rn(v[i], 127.5f), 127.5f), 0.f), 255.f);
+      dst[3 * i] = static_cast<uint8_t>(s);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1210,8 +1226,10 @@ int blur_up_fused_launch(const float* t_cl, int B, int C, int Hin, int Win, cons
 }
 
 int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const float* bias,
-                       const float* prev, const float* k4, float* out, cudaStream_t stream) {
+                       const float* prev, const float* k4, float* out, unsigned char* out_u8,
+                       cudaStream_t stream) {
   if ((W & 3) != 0 || (prev && ((H | W) & 1)) || static_cast<long long>(B) * 3 > 65535 ||
+      (!out && !out_u8) ||
       (reinterpret_cast<uintptr_t>(part) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) {
     set_last_error("rgb_combine: W=%d must be a multiple of 4 (even H, W with a skip), B*3 <= 65535, "
                    "16-byte aligned buffers", W);
@@ -1224,7 +1242,7 @@ int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const
   dim3 grid((quads + bx - 1) / bx, (H + by - 1) / by, B * 3);
   const long long part_stride = static_cast<long long>(B) * 3 * H * W;
   rgb_combine_kernel<<<grid, block, 0, stream>>>(part, nparts, part_stride, H, W, bias, prev, k4,
-                                                 out);
+                                                 out, out_u8);
   return check_cuda(cudaGetLastError(), "rgb_combine launch");
 }
 

@@ -83,6 +83,19 @@ def eligible(model, z):
     return _layer_list(model) is not None
 
 
+import os as _os
+
+# RW_UP_FUSED=0 keeps the round-1 pair (conv_transpose phases -> channels-last t -> blur kernel);
+# RW_UP_FUSED_MINW = smallest input width that takes the fused kernel
+_UP_FUSED = _os.environ.get('RW_UP_FUSED', '1') != '0'
+_UP_FUSED_MINW = int(_os.environ.get('RW_UP_FUSED_MINW', '4'))
+
+
+def _use_fused_up(mc, Cin, Cout, H, W):
+    return (_UP_FUSED and H == W and _UP_FUSED_MINW <= W <= 128 and (W & (W - 1)) == 0 and
+            Cin % 64 == 0 and Cout % 16 == 0 and ops.blur_is_separable(mc.blur.kernel))
+
+
 def _mapping(model, z, stream):
     """w = AdjustLatent(style MLP(z)) as [B, style_dim] (models.py:487-533,570-583,609-614):
     PixelNorm + one fused EqualLinear(lrelu) launch per layer instead of sgemm + bias_act + two
@@ -110,8 +123,11 @@ def _mapping(model, z, stream):
     return x
 
 
-def forward(model, z, upto_key_layer=None):
-    """image [B,3,size,size] (or KeyPlanes of `layer<upto_key_layer>`'s key)."""
+def forward(model, z, upto_key_layer=None, noise_period=None, out_u8=False):
+    """image [B,3,size,size] (or KeyPlanes of `layer<upto_key_layer>`'s key).
+    `noise_period`: sample i takes the noise row (i % noise_period) — see ops.noise_table.
+    `out_u8`: return the image as NHWC uint8, clamp(x*127.5+127.5, 0, 255), written by the last
+    ToRGB combine (the fp32 image is then never stored)."""
     from .utils.stylegan2 import models as sg2
     layers = _layer_list(model)
     if layers is None:
@@ -192,13 +208,26 @@ def forward(model, z, upto_key_layer=None):
         next_scale = styles[nxt[0]] if nxt is not None else None
         nw = sconv.noise.weight.detach()
         bias = sconv.activate.bias.detach()
-        if mc.upsample:
+        if mc.upsample and _use_fused_up(mc, Cin, Cout, H, W):
+            # conv_transpose + blur + noise + bias + act + next style in ONE tensor-core kernel
+            u_hi, u_lo, _ = ops.weight_planes(dconv.weight, 'upf')
+            Ho, Wo = 2 * H, 2 * W
+            noise = ops.noise_table(B, Ho * Wo, dev, noise_period)
+            rows_o = B * (Ho + 1) * (Wo + 1)
+            nh = torch.empty((rows_o, Cout), dtype=torch.bfloat16, device=dev)
+            nl = torch.empty_like(nh)
+            _cabi.call('rw_modconv_up_fused', _p(planes.hi), _p(planes.lo), _p(u_hi), _p(u_lo),
+                       _p(dm), _p(mc.blur.kernel), _p(noise), noise.stride(0), _p(nw), _p(bias),
+                       _p(next_scale), _p(nh), _p(nl), B, Cin, Cout, H, W, stream)
+            H, W = Ho, Wo
+            planes = ops.KeyPlanes(nh, nl, B, Cout, H, W)
+        elif mc.upsample:
             rows = B * (H + 1) * (W + 1)
             t_cl = torch.empty((4, rows, Cout), dtype=torch.float32, device=dev)
             _cabi.call('rw_modconv_up_fwd_cl', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
                        _p(dm), B, Cin, Cout, H, W, _p(t_cl), stream)
             Ho, Wo = 2 * H, 2 * W
-            noise = ops.noise_table(B, Ho * Wo, dev)
+            noise = ops.noise_table(B, Ho * Wo, dev, noise_period)
             rows_o = B * (Ho + 1) * (Wo + 1)
             nh = torch.empty((rows_o, Cout), dtype=torch.bfloat16, device=dev)
             nl = torch.empty_like(nh)
@@ -208,7 +237,7 @@ def forward(model, z, upto_key_layer=None):
             H, W = Ho, Wo
             planes = ops.KeyPlanes(nh, nl, B, Cout, H, W)
         else:
-            noise = ops.noise_table(B, H * W, dev)
+            noise = ops.noise_table(B, H * W, dev, noise_period)
             rows = B * (H + 1) * (W + 1)
             nh = nl = None
             if nxt is not None:
@@ -223,13 +252,20 @@ def forward(model, z, upto_key_layer=None):
                        _p(dm), _p(noise), noise.stride(0), _p(nw), _p(bias), 1, B, Cin, Cout, H, W,
                        None, _p(next_scale), _p(nh), _p(nl), _p(rgb_w), _p(rgb_part), stream)
             if rgb is not None:
-                out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+                last = out_u8 and nxt is None
+                out = None if last else torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
                 up_k = None
                 if image is not None:
                     up_k = model._modules['up_rgb%d' % (num // 2 - 1)].kernel
-                _cabi.call('rw_rgb_combine', _p(rgb_part), ntile, B, H, W,
-                           _p(rgb.bias.detach().reshape(3).contiguous()), _p(image), _p(up_k),
-                           _p(out), stream)
+                if last:
+                    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+                    _cabi.call('rw_rgb_combine_u8', _p(rgb_part), ntile, B, H, W,
+                               _p(rgb.bias.detach().reshape(3).contiguous()), _p(image), _p(up_k),
+                               None, _p(out), stream)
+                else:
+                    _cabi.call('rw_rgb_combine', _p(rgb_part), ntile, B, H, W,
+                               _p(rgb.bias.detach().reshape(3).contiguous()), _p(image), _p(up_k),
+                               _p(out), stream)
                 image = out
             if nxt is not None:
                 planes = ops.KeyPlanes(nh, nl, B, Cout, H, W)

@@ -44,19 +44,37 @@ def _f32c(t):
 _NOISE_CACHE = {}
 
 
-def noise_table(batch, hw, device):
+def noise_table(batch, hw, device, period=None):
     """The reference draws `np.random.RandomState(0).randn(batch, H*W)` on the host in
     every NoiseInjectionF.forward (models.py:542-545).  The values only depend on
-    (batch, H*W); generate once and keep on the device."""
-    key = (batch, hw, str(device))
+    (batch, H*W); generate once and keep on the device.
+
+    `period`: row i of the table is row (i % period) of `randn(period, H*W)` — what sample i of a
+    stream gets when the reference processes it in batches of `period` (its tally loops use 10).
+    Lets a large batch reproduce the reference's small-batch statistics exactly."""
+    if period is not None and period >= batch:
+        period = None
+    key = (batch, hw, str(device), period)
     t = _NOISE_CACHE.get(key)
     if t is None:
-        arr = np.random.RandomState(0).randn(batch, hw).astype('float32')
+        if period is None:
+            arr = np.random.RandomState(0).randn(batch, hw).astype('float32')
+        else:
+            base = np.random.RandomState(0).randn(period, hw).astype('float32')
+            arr = np.ascontiguousarray(base[np.arange(batch) % period])
         t = torch.from_numpy(arr).to(device)
-        if len(_NOISE_CACHE) > 64:
-            _NOISE_CACHE.clear()
+        while len(_NOISE_CACHE) > 256:            # evict the oldest entry only; live CUDA graphs
+            _NOISE_CACHE.pop(next(iter(_NOISE_CACHE)))   # keep their tables alive themselves
         _NOISE_CACHE[key] = t
     return t
+
+
+def cached_device_state():
+    """Every cached device tensor whose raw pointer a captured CUDA graph may have baked in
+    (noise tables, weight planes, workspaces).  `GraphedModule` holds this list so that a cache
+    eviction can never free memory a graph replay still reads."""
+    return (list(_NOISE_CACHE.values()), [e[2] for e in _WEIGHT_CACHE.values()],
+            list(_WS.values()))
 
 
 # --------------------------------------------------------------------------- planes
@@ -119,6 +137,10 @@ def weight_planes(weight, kind='fwd'):
         wsq = torch.empty((Cout, Cin), dtype=torch.float32, device=w.device)
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 0, 0, _p(hi), _p(lo), _p(wsq),
                    _stream())
+    elif kind == 'upf':        # [Cout/16][tap][16][Cin]: N = 144 tiles of the fused up-conv
+        wsq = weight_planes(weight, 'fwd')[2]
+        _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 2, 0, _p(hi), _p(lo), None,
+                   _stream())
     elif kind == 'dgrad':      # [Cin][flipped tap][Cout]
         wsq = None
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 1, 1, _p(hi), _p(lo), None,
@@ -131,8 +153,8 @@ def weight_planes(weight, kind='fwd'):
         raise ValueError(kind)
     val = (hi, lo, wsq)
     if isinstance(weight, torch.nn.Parameter):
-        if len(_WEIGHT_CACHE) > 256:
-            _WEIGHT_CACHE.clear()
+        while len(_WEIGHT_CACHE) > 256:
+            _WEIGHT_CACHE.pop(next(iter(_WEIGHT_CACHE)))
         _WEIGHT_CACHE[key] = (weakref.ref(weight), weight._version, val)
     return val
 
@@ -144,6 +166,25 @@ def demod_factors(style, wsq, eps=1e-8):
     out = torch.empty((B, Cout), dtype=torch.float32, device=style.device)
     _cabi.call('rw_demod', _p(style), _p(wsq), B, Cout, Cin, eps, _p(out), _stream())
     return out
+
+
+_SEPARABLE = {}
+
+
+def blur_is_separable(kernel):
+    """True if the 4x4 FIR is rank one (the model's [1,3,3,1] x [1,3,3,1] always is), which the
+    fused upsampling kernel requires.  One device->host read per kernel tensor version (done in
+    the warm-up pass, never inside a graph capture)."""
+    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+    r = _SEPARABLE.get(key)
+    if r is None:
+        k = kernel.detach().double().cpu()
+        r = bool(tuple(k.shape) == (4, 4) and k[0, 0] != 0 and
+                 torch.equal(k * k[0, 0], torch.outer(k[:, 0], k[0, :])))
+        if len(_SEPARABLE) > 64:
+            _SEPARABLE.clear()
+        _SEPARABLE[key] = r
+    return r
 
 
 # --------------------------------------------------------------------------- conv kernels

@@ -133,10 +133,14 @@ class ProgressiveGanRewriter(object):
 
     # ---------------------------------------------------------------------------- statistics
     # z per context pass of the covariance collection.  The reference tallies batches of 10
-    # (tally.py:424-443); C is a plain sum over samples, so the batch size only changes the fp32
-    # summation order (C rel-Frobenius ~1e-7).  The fused key capture is launch- and tail-bound
-    # below a few hundred z per pass (the 4x4..16x16 convs are a handful of tiles each).
-    FAST_MOMENT_BATCH = 256
+    # (tally.py:424-443), and through NoiseInjectionF's `RandomState(0).randn(batch, H*W)` the
+    # noise a sample sees is row (index % 10) of that table: a larger pass reproduces it with a
+    # 10-periodic noise table (ops.noise_table(period=10)) and pass sizes that are multiples of
+    # 10; the sum over samples then only differs in fp32 summation order (C rel-Frobenius ~1e-7).
+    # The fused key capture is launch- and tail-bound below a few hundred z per pass (the
+    # 4x4..16x16 convs are a handful of tiles each).
+    FAST_MOMENT_BATCH = 250
+    REFERENCE_TALLY_BATCH = 10
 
     def _fast_key_layer(self):
         """N if the keys are the operand planes of `layerN...dconv` of an intact SeqStyleGAN2
@@ -160,7 +164,8 @@ class ProgressiveGanRewriter(object):
         if layer is not None and fastpath.eligible(self.model, z):
             if z.shape[0] == getattr(self, '_moment_bs', None):
                 return self._graphed_key_planes(z, layer)
-            return fastpath.forward(self.model, z, upto_key_layer=layer)   # ragged last batch
+            return fastpath.forward(self.model, z, upto_key_layer=layer,  # ragged last batch
+                                    noise_period=self.REFERENCE_TALLY_BATCH)
         acts = self.context_acts(self.context_model(z))
         planes, _ = ops.prep_keys(acts, None)
         return planes
@@ -176,8 +181,9 @@ class ProgressiveGanRewriter(object):
         ent = cache.get(key)
         if ent is None or ent[0] != versions:
             model = self.model
-            fn = lambda zz: fastpath.forward(model, zz, upto_key_layer=layer)
-            ent = (versions, GraphedModule(fn, z))
+            period = self.REFERENCE_TALLY_BATCH
+            fn = lambda zz: fastpath.forward(model, zz, upto_key_layer=layer, noise_period=period)
+            ent = (versions, GraphedModule(fn, z, parameters=model.parameters))
             cache[key] = ent
         return ent[1](z)
 
@@ -190,8 +196,10 @@ class ProgressiveGanRewriter(object):
         if batch_size is None:
             batch_size = 10
             if self._fast_key_layer() is not None:
+                t = self.REFERENCE_TALLY_BATCH
                 per_rank = -(-len(self.zds) // R)
-                batch_size = max(1, min(self.FAST_MOMENT_BATCH, per_rank))
+                per_rank = -(-per_rank // t) * t           # whole reference batches per pass
+                batch_size = max(t, min(self.FAST_MOMENT_BATCH, per_rank))
         self._moment_bs = batch_size
         with torch.no_grad(), pbar.quiet():
             if R > 1:
@@ -373,6 +381,10 @@ class ProgressiveGanRewriter(object):
         B, Cin, h, w = k.shape
         if B > 4 or w > 16 or B * h * w > 4096 or Cin % 32 != 0 or context.shape[0] > 32:
             return None
+        # shared memory of rw_insert_loop (csrc/rewrite.cu insert_loop_launch): 4 weight rows +
+        # 4 gradient rows + 8 crop-sized vectors + small tables, within 225 KB
+        if (8 * Cin * 9 + 8 * B * h * w + 1440) * 4 > 225 * 1024:
+            return None
         if tuple(self.target_acts(val).shape) != (B, dconv.out_channel, h, w):
             return None
         return dconv, nz, act
@@ -414,6 +426,12 @@ class ProgressiveGanRewriter(object):
             args.loss_out = loss_buf.data_ptr()
             args.noise_w = float(nz.weight.item()) if nz is not None else 0.0
             args.lr, args.beta1, args.beta2, args.eps = float(lr), 0.9, 0.999, 1e-8
+            # torch.optim.Adam forms (1 - beta) in Python doubles and rounds once to fp32
+            # (a kernel that derives everything from float(0.9), float(0.999) is self-consistent
+            #  and tracks torch too; mixing float betas in the bias corrections with exact 1-beta
+            #  is what drifts: 6e-6 relative in the first denominators, 4e-3 on W after 11 steps)
+            args.one_minus_beta1, args.one_minus_beta2 = 1 - 0.9, 1 - 0.999
+            args.beta1_exact, args.beta2_exact = 0.9, 0.999
             args.rank, args.B, args.Cin, args.Cout, args.h, args.w = d.shape[0], B, Cin, Cout, h, w
             args.has_noise_act = 1 if nz is not None else 0
             args.niter_total, args.piter = niter, piter

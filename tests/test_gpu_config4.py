@@ -1,0 +1,155 @@
+"""GPU (B200): BASELINE config 4 on its own fixture and horizon —
+notebooks/masks/stylegan/horse/hat_on_horse_ears.json, 1000 z, layer 8, rank 1, 4 context keys,
+2001 iterations (reference: ganrewrite.py:135-169, 254-298, 333-374) — against the goldens the
+live reference produced (oracle/make_golden_config4.py) and the fp64-anchored protocol of
+SURVEY.md §7(ii)."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def c4():
+    return dict(np.load(os.path.join(GOLD, 'config4_hat.npz')))
+
+
+@pytest.fixture(scope='module')
+def hat_request():
+    with open(os.path.join(GOLD, 'hat_on_horse_ears.json')) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='module')
+def gw1000(seeded_model):
+    from rewriting_b200.rewrite import ganrewrite
+    from rewriting_b200.utils import zdataset
+    model = copy.deepcopy(seeded_model).cuda().eval()
+    zds = torch.utils.data.TensorDataset(zdataset.standard_z_sample(1000, 512, seed=1))
+    return ganrewrite.SeqStyleGanRewriter(model, zds, 8)
+
+
+def _lam(W, W0, d):
+    return torch.einsum('goiyx,i->goyx', (W - W0).double(), d[0].double())[0]
+
+
+def test_covariance_over_1000_z_matches_the_reference(gw1000, c4):
+    """C = E[kk^T] collected in passes of 250 z (10-periodic noise table) vs the reference's
+    batches of 10 (ganrewrite.py:83-96, tally.py:424-443)."""
+    C = gw1000.c_matrix.double().cpu()
+    Cg = torch.from_numpy(c4['C']).double()
+    rel = ((C - Cg).norm() / Cg.norm()).item()
+    assert rel < 5e-5, rel
+    np.testing.assert_allclose(C.diag().numpy(), Cg.diag().numpy(), rtol=2e-4)
+    assert torch.equal(gw1000.c_matrix, gw1000.c_matrix.t())
+
+
+def test_goal_crops_and_direction(gw1000, c4, hat_request):
+    gw = gw1000
+    obj_acts, _, obj_area, ob = gw.object_from_selection(*hat_request['object'])
+    goal_in, goal_out, _, pb = gw.paste_from_selection(
+        hat_request['paste'][0], hat_request['paste'][1], obj_acts, obj_area)
+    assert tuple(ob) == tuple(c4['obj_bounds']) and tuple(pb) == tuple(c4['paste_bounds'])
+    assert (goal_in.fmap.cpu() - torch.from_numpy(c4['goal_in_fmap'])).abs().max() < 1e-3
+    assert (goal_out.fmap.cpu() - torch.from_numpy(c4['goal_out_fmap'])).abs().max() < 1e-3
+    assert (goal_in.style.cpu() - torch.from_numpy(c4['goal_in_style'])).abs().max() < 1e-4
+    d_gold = torch.from_numpy(c4['d'])
+    d = gw.multi_key_from_selection(hat_request['key'], rank=1).cpu()
+    assert float((d[0] * d_gold[0]).sum()) > 1 - 1e-5        # end to end (own C), as a direction
+    # the key algebra itself on the reference's C: within 1e-4
+    keep = gw.c_matrix, gw.zca_matrix
+    try:
+        from rewriting_b200.rewrite import ganrewrite
+        gw.c_matrix = torch.from_numpy(c4['C']).cuda()
+        gw.zca_matrix = ganrewrite.zca_from_cov(gw.c_matrix)
+        d_same = gw.multi_key_from_selection(hat_request['key'], rank=1).cpu()
+    finally:
+        gw.c_matrix, gw.zca_matrix = keep
+    assert (d_same - d_gold).abs().max().item() < 1e-4
+
+
+def _goal_bags(gw, c4):
+    bag = gw.context_model(gw.get_z(854))
+    gin = type(bag)(bag, fmap=torch.from_numpy(c4['goal_in_fmap']).cuda(),
+                    style=torch.from_numpy(c4['goal_in_style']).cuda())
+    gout = type(bag)(bag, fmap=torch.from_numpy(c4['goal_out_fmap']).cuda())
+    return gin, gout
+
+
+def test_edit_50_iterations_within_1e4(gw1000, c4):
+    """identical state, identical d as the reference run: edited W within 1e-4 (short horizon)"""
+    gw = gw1000
+    gin, gout = _goal_bags(gw, c4)
+    d = torch.from_numpy(c4['d']).cuda()
+    W0 = gw.target_weights().detach().clone()
+    losses = []
+    try:
+        gw.insert(gin, gout, d, niter=50, piter=10, lr=0.05,
+                  update_callback=lambda it, loss: losses.append(float(loss)))
+        W = gw.target_weights().detach().clone()
+    finally:
+        with torch.no_grad():
+            gw.target_weights()[...] = W0
+    lam_ref = torch.from_numpy(c4['lam50']).double()
+    dW_ref = torch.einsum('oyx,i->oiyx', lam_ref, torch.from_numpy(c4['d'])[0].double())
+    err = ((W - W0)[0].double().cpu() - dW_ref).abs().max().item()
+    assert err < 1e-4, err
+    np.testing.assert_allclose(np.array(losses), c4['loss50'], rtol=2e-4)
+
+
+def test_edit_2001_iterations_fp64_anchored(gw1000, c4):
+    """the reference's own fp32 run deviates from its fp64 run (here 2.7e-3
+    rel-Frobenius, final loss 0.2 %); the fused loop must stay within the same budget: deviation
+    from the fp64 anchor <= 2e-2 rel-Frobenius, final loss within 1 %, delta W exactly rank one."""
+    gw = gw1000
+    gin, gout = _goal_bags(gw, c4)
+    d = torch.from_numpy(c4['d']).cuda()
+    W0 = gw.target_weights().detach().clone()
+    losses = []
+    try:
+        gw.insert(gin, gout, d, niter=2001, piter=10, lr=0.05,
+                  update_callback=lambda it, loss: losses.append(float(loss)))
+        W = gw.target_weights().detach().clone()
+    finally:
+        with torch.no_grad():
+            gw.target_weights()[...] = W0
+    assert len(losses) == 2001
+    lam = _lam(W.cpu(), W0.cpu(), torch.from_numpy(c4['d']))
+    lam64 = torch.from_numpy(c4['lam2001_fp64']).double()
+    rel = ((lam - lam64).norm() / lam64.norm()).item()
+    assert rel < 2e-2, rel
+    assert rel < 10 * float(c4['rel_fro_ref32_vs_fp64']) + 1e-3     # same order as the reference's own
+    assert abs(losses[-1] - float(c4['final_loss_fp64'])) < 1e-2 * float(c4['final_loss_fp64'])
+    np.testing.assert_allclose(np.array(losses)[::10][:20], c4['loss2001_ref32'][:20], rtol=2e-3)
+    dW = (W - W0)[0].permute(0, 2, 3, 1).reshape(-1, 512).double().cpu()
+    s = torch.linalg.svdvals(dW)
+    assert float(s[1] / s[0]) < 1e-6
+    assert abs(dW.abs().max().item() - float(c4['max_abs_dW_2001'])) < 0.1 * float(c4['max_abs_dW_2001'])
+
+
+def test_apply_edit_public_call(gw1000, c4, hat_request):
+    """gw.apply_edit(request, rank=1) end to end (own C, own d, own crops), 2001 iterations"""
+    gw = gw1000
+    W0 = gw.target_weights().detach().clone()
+    losses = []
+    try:
+        gw.apply_edit(hat_request, rank=1, niter=2001, piter=10, lr=0.05,
+                      update_callback=lambda it, loss: losses.append(float(loss)))
+        W = gw.target_weights().detach().clone()
+        with torch.no_grad():
+            img = gw.sample_image_from_latent(gw.get_z(854))
+    finally:
+        with torch.no_grad():
+            gw.target_weights()[...] = W0
+    assert torch.isfinite(img).all()
+    assert abs(losses[-1] - float(c4['final_loss_ref32'])) < 2e-2 * float(c4['final_loss_ref32'])
+    dW = (W - W0)[0].permute(0, 2, 3, 1).reshape(-1, 512).double().cpu()
+    s = torch.linalg.svdvals(dW)
+    assert float(s[1] / s[0]) < 1e-6

@@ -142,3 +142,51 @@ def test_blur_up_fused_vs_layer_kernels(B, C, H, W, separable):
         assert (got - ref).abs().max().item() < 3e-5 * max(1.0, ref.abs().max().item()), with_y
         v = got.view(B, Ho + 1, Wo + 1, C)
         assert v[:, Ho].abs().max() == 0 and v[:, :, Wo].abs().max() == 0   # pad row / column
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H', [(2, 64, 16, 4), (3, 128, 32, 8), (5, 64, 48, 16),
+                                          (2, 128, 32, 32), (3, 64, 16, 64), (2, 64, 32, 128),
+                                          (33, 64, 16, 4)])
+def test_modconv_up_fused_vs_oracle(B, Cin, Cout, H):
+    """ONE kernel for conv_transpose + blur + demod + noise + bias + leaky-ReLU + next style ->
+    bf16 planes (csrc/upconv_tc.cu) against the oracle's DemodulatedConv2dF(upsample) -> BlurF ->
+    NoiseInjectionF -> FusedLeakyReLUF chain (models.py:313-329, 275-281, 535-546) on the CPU."""
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(4 + H)
+    dev = 'cuda'
+    W = H
+    x = torch.randn(B, Cin, H, W)
+    style = torch.randn(B, Cin) * 0.5 + 1
+    weight = torch.randn(1, Cout, Cin, 3, 3)
+    nw = torch.tensor([0.37])
+    bias = torch.randn(Cout)
+    nscale = torch.randn(B, Cout) * 0.5 + 1
+    kern = orc.make_kernel([1, 3, 3, 1]) * 4
+    # oracle (CPU fp32)
+    k = style[:, :, None, None] * x
+    t = orc.demod_conv(k, style, weight, True)
+    t = orc.upfirdn2d(t, kern, pad=(1, 1))
+    Ho, Wo = 2 * H, 2 * W
+    n = orc.noise_table(B, Ho * Wo).view(B, 1, Ho, Wo)
+    want = orc.fused_leaky_relu(t + nw * n, bias) * nscale[:, :, None, None]
+    # device
+    planes, _ = ops.prep_keys(x.to(dev), style.to(dev))
+    wp = torch.nn.Parameter(weight.to(dev))
+    u_hi, u_lo, wsq = ops.weight_planes(wp, 'upf')
+    dm = ops.demod_factors(style.to(dev), wsq)
+    noise = ops.noise_table(B, Ho * Wo, dev)
+    rows_o = B * (Ho + 1) * (Wo + 1)
+    nh = torch.full((rows_o, Cout), float('nan'), dtype=torch.bfloat16, device=dev)
+    nl = torch.full_like(nh, float('nan'))
+    kern_d, nw_d, bias_d, nscale_d = kern.to(dev), nw.to(dev), bias.to(dev), nscale.to(dev)
+    _cabi.call('rw_modconv_up_fused', ops._p(planes.hi), ops._p(planes.lo), ops._p(u_hi),
+               ops._p(u_lo), ops._p(dm), ops._p(kern_d), ops._p(noise), noise.stride(0),
+               ops._p(nw_d), ops._p(bias_d), ops._p(nscale_d), ops._p(nh), ops._p(nl), B, Cin, Cout,
+               H, W, ops._stream())
+    torch.cuda.synchronize()
+    got = (nh.float() + nl.float()).cpu().view(B, Ho + 1, Wo + 1, Cout)
+    assert torch.isfinite(got).all()                      # every row written, pads included
+    assert got[:, Ho].abs().max() == 0 and got[:, :, Wo].abs().max() == 0   # pad row / column
+    got = got[:, :Ho, :Wo].permute(0, 3, 1, 2)
+    err = (got - want).abs().max().item()
+    assert err < 2e-4 * max(1.0, want.abs().max().item()), err

@@ -491,10 +491,54 @@ def test_bulk_sampling_matches_reference_seed_rule(cuda_model, seeded_sd):
     with torch.no_grad():
         ref = orc.generator_forward(seeded_sd, z1)
     assert (imgs[2:4] - ref).abs().max().item() < 1e-3
+    # uint8 NHWC straight from the last ToRGB combine: exactly clamp(x*127.5+127.5).byte() of
+    # this path's own fp32 image ...
     u8, _ = sampling.get_samples(cuda_model, nimgs=2, batch=2, out_dtype=torch.uint8,
                                  reference_count=False)
-    want = (imgs[0:2] * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)
-    assert u8.shape == (2, 3, 256, 256) and (u8.int() - want.int()).abs().max().item() <= 1
+    want = (imgs[0:2] * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert u8.shape == (2, 256, 256, 3) and u8.dtype == torch.uint8
+    assert torch.equal(u8, want)
+    # ... and of the oracle's image up to the 1e-3 pixel tolerance (a byte flips where the
+    # fp32 value sits on an integer boundary)
+    with torch.no_grad():
+        ref0 = orc.generator_forward(seeded_sd, sampling.z_for_batch(0, 2))
+    ref_u8 = (ref0 * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    d = (u8.int() - ref_u8.int()).abs()
+    assert d.max().item() <= 1 and (d > 0).float().mean().item() < 0.02
+    # several reference batches per replay (noise rows repeat with the reference batch size)
+    # give the same images as one reference batch per replay
+    g1, _ = sampling.get_samples(cuda_model, nimgs=4, batch=2, group=1)
+    assert torch.equal(g1, imgs)
+
+
+def test_sample_loop_batch1_seed_imgnum_and_writer(cuda_model, seeded_sd, tmp_path):
+    """metrics/sample.py:19-37: image n = G(z_sample(1, seed=n+offset)) run as a batch of one;
+    32 per replay here with a period-1 noise table.  Writer: PNG per image / one npz."""
+    import numpy as np
+    from PIL import Image
+    from rewriting_b200 import sampling
+    from rewriting_b200.utils import zdataset
+    nums = [0, 1, 2, 5, 7]
+    u8, mine = sampling.sample_images(cuda_model, nums, offset=1000007, group=3)
+    assert mine == nums and u8.shape == (5, 256, 256, 3) and u8.dtype == torch.uint8
+    for i in (1, 4):
+        z = zdataset.standard_z_sample(1, 512, seed=nums[i] + 1000007)
+        with torch.no_grad():
+            ref = orc.generator_forward(seeded_sd, z)
+        ref_u8 = (ref * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)[0]
+        d = (u8[i].int() - ref_u8.int()).abs()
+        assert d.max().item() <= 1 and (d > 0).float().mean().item() < 0.02, i
+    w = sampling.ImageWriter(str(tmp_path / 'png'), fmt='png', workers=2)
+    w.add(u8, mine)
+    w.join()
+    back = np.array(Image.open(str(tmp_path / 'png' / '5.png')))
+    assert np.array_equal(back, u8[3].numpy())
+    w = sampling.ImageWriter(str(tmp_path / 'npz'), fmt='npz')
+    w.add(u8[:2], mine[:2])
+    w.add(u8[2:], mine[2:])
+    w.join()
+    dat = np.load(str(tmp_path / 'npz' / 'images.npz'))
+    assert np.array_equal(dat['images'], u8.numpy()) and list(dat['imgnums']) == nums
 
 
 def test_ui_search_ranking_and_unit_quantiles_vs_oracle(cuda_model, z40, golden, seeded_sd):

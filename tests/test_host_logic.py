@@ -250,3 +250,27 @@ print('ok')
     r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
+
+
+def test_frechet_statistics_match_the_scipy_formula():
+    """sampling.frechet_distance / activation_statistics vs the reference's numpy + scipy
+    formula (metrics/fid.py:137-175: sqrtm of the covariance product)."""
+    import numpy as np
+    from scipy import linalg
+    from rewriting_b200 import sampling
+    rng = np.random.RandomState(0)
+    a = rng.randn(500, 24) @ rng.randn(24, 24)
+    b = rng.randn(400, 24) @ rng.randn(24, 24) + 0.3
+    mu1, s1 = sampling.activation_statistics(torch.from_numpy(a))
+    mu2, s2 = sampling.activation_statistics(torch.from_numpy(b))
+    np.testing.assert_allclose(s1.numpy(), np.cov(a, rowvar=False), rtol=1e-10, atol=1e-12)
+    covmean = linalg.sqrtm(np.cov(a, rowvar=False).dot(np.cov(b, rowvar=False)))
+    diff = a.mean(0) - b.mean(0)
+    want = diff.dot(diff) + np.trace(np.cov(a, rowvar=False)) + np.trace(np.cov(b, rowvar=False)) \
+        - 2 * np.trace(covmean.real)
+    got = sampling.frechet_distance(mu1, s1, mu2, s2)
+    assert abs(got - want) < 1e-6 * max(1.0, abs(want))
+    img = torch.rand(2, 3, 4, 4) * 2 - 1
+    f = sampling.pt_to_float255_nhwc(img)
+    assert f.shape == (2, 4, 4, 3) and float(f.min()) >= 0 and float(f.max()) <= 255
+    assert torch.allclose(f[0, 1, 2], ((img[0, :, 1, 2] / 2 + 0.5) * 255))
