@@ -10,9 +10,15 @@ step     : one batch of 32 latents through the whole generator -> 32 images (per
 value    : images/s with z resident in HBM, CUDA-event timed, max over ranks, whole job
 e2e      : same through the public API with HOST buffers: pinned z -> H2D, model(z), D2H of
            the images into pinned memory, inside the timed region
-extra    : key-covariance samples/sec (layer 8, BASELINE.json's second metric): context
-           forward + tensor-core second moment per batch of z, one all-reduce of (mom2,count)
-           at the end; rewrite-loop iterations/sec (1 GPU, "replicas only")
+extra    : the other BASELINE.json configs as stated —
+           config 3: key-covariance samples/sec, layer 8, 10 000 z through
+             SeqStyleGanRewriter.collect_2nd_moment, STRONG scaling over the ranks, the one
+             all-reduce of (mom2, count) inside the timing (also reported as `roofline_cov`);
+           config 4: the shipped hat_on_horse_ears.json request, 1000 z, 2001 iterations:
+             apply_edit (key finding + insert) and the insert loop alone, its/s ("replicas only");
+           config 5: 50 010 images (reference batches of 10, seed 10*j) sharded over the ranks,
+             uint8 NHWC out, pipelined D2H;
+           config 2: fused StyledConv forward + backward over all 13 layer shapes (N = 1 only)
 roofline : dominant kernel = conv_tc (implicit-GEMM styled conv); achieved = algorithmic conv
            FLOPs / summed CUDA-event kernel time, against the MEASURED bf16 tensor peak
 cpu_baseline / --impl reference: the CPU oracle port of the reference's PyTorch path
@@ -34,12 +40,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def cpu_threads():
+    """torch CPU convs at batch 2 stop scaling past ~16 threads (measured on the 128-core GPU
+    host: 8 thr 1.11 s, 16 thr 0.96 s, 32 thr 0.98 s, 64 thr 1.41 s, 128 thr 19 s per forward),
+    so the baseline uses the fastest setting, not the core count."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU-baseline legs (rank 0 only) would
+# then run single-threaded inside MKL/oneDNN whatever torch.set_num_threads says later
+if os.environ.get('OMP_NUM_THREADS', '1') == '1':
+    os.environ['OMP_NUM_THREADS'] = str(cpu_threads())
+    os.environ.setdefault('MKL_NUM_THREADS', str(cpu_threads()))
+
 import torch  # noqa: E402
 
 BATCH = 32
-COV_BATCH = 32
 SIZE = 256
 GFLOP_PER_IMG = 90.24          # algorithmic conv FLOPs of one 256^2 forward (SURVEY.md App. A)
+GFLOP_PER_COV_SAMPLE = 3.71    # context forward to layer 8 + key second moment, per z (§8d)
+N_COV = 10000                  # BASELINE config 3
+N_SAMPLE_IMAGES = 50000        # BASELINE config 5 (the reference generates 50 010)
 METRIC = 'StyleGAN2-256 images/sec'
 
 
@@ -121,18 +143,9 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_threads():
-    """torch CPU convs at batch 2 stop scaling past ~16 threads (measured on the 128-core GPU
-    host: 8 thr 1.11 s, 16 thr 0.96 s, 32 thr 0.98 s, 64 thr 1.41 s, 128 thr 19 s per forward),
-    so the baseline uses the fastest setting, not the core count."""
-    return max(1, min(os.cpu_count() or 1, 16))
-
-
 def build_model(device):
-    from oracle import sg2_oracle as orc      # only for the seeded-weights recipe (no compute)
-    from rewriting_b200.utils.stylegan2 import SeqStyleGAN2
-    model = orc.seeded_state_dict(lambda: SeqStyleGAN2(SIZE, style_dim=512, n_mlp=8, mconv='seq'))
-    return model.to(device).eval()
+    from rewriting_b200.synthetic import seeded_generator    # the product arm imports no oracle/
+    return seeded_generator(SIZE).to(device).eval()
 
 
 def cpu_baseline_generator(seconds=12.0, batch=2):
@@ -236,6 +249,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-extra', action='store_true', help='skip covariance / insert extras')
+    ap.add_argument('--sample-images', type=int, default=N_SAMPLE_IMAGES,
+                    help='images of the config-5 sampling leg (0 skips it)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true',
                     help='time eager module calls instead of the CUDA-graph replay')
@@ -288,7 +303,8 @@ def main():
     conv_events = []
     timing_on = {'on': False}
     CONV_ENTRY = {'rw_modconv_fwd': (10, 11, 12, 13, 14), 'rw_modconv_fwd_fused': (10, 11, 12, 13, 14),
-                  'rw_modconv_up_fwd': (5, 6, 7, 8, 9), 'rw_modconv_up_fwd_cl': (5, 6, 7, 8, 9)}
+                  'rw_modconv_up_fwd': (5, 6, 7, 8, 9), 'rw_modconv_up_fwd_cl': (5, 6, 7, 8, 9),
+                  'rw_modconv_up_fused': (13, 14, 15, 16, 17)}
     orig_call = _cabi.call
 
     def timed_call(name, *a):
@@ -382,50 +398,31 @@ def main():
     value = BATCH * K * world / (ms_dev / 1e3)
     e2e_value = BATCH * K * world / (ms_e2e / 1e3)
 
-    # ---- extras: covariance samples/s and rewrite-loop its/s --------------------------------
+    # ---- extras: BASELINE configs 3, 4, 5 as stated, and config 2 --------------------------
     extra = {}
+    cov = None
     if not args.no_extra:
-        from rewriting_b200 import fastpath
-        with torch.no_grad():
-            # what SeqStyleGanRewriter.collect_2nd_moment does per batch: generator up to layer
-            # 8's conv (CUDA-graph replay), whose operand planes are the keys, then the col-GEMM
-            key_runner = GraphedModule(lambda zz: fastpath.forward(model, zz, upto_key_layer=8),
-                                       z_dev[:COV_BATCH])
-
-            def cov_step(zb, r2m):
-                planes = key_runner(zb)
-                r2m.add_planes(planes.hi, planes.lo, planes.B * planes.H * planes.W)
-            r2m = runningstats.RunningSecondMoment()
-            for i in range(W):
-                cov_step(z_dev[i * COV_BATCH:(i + 1) * COV_BATCH], r2m)
-            r2m = runningstats.RunningSecondMoment()
-            barrier()
-            c0 = torch.cuda.Event(enable_timing=True)
-            c1 = torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for i in range(W, W + K):
-                flush.zero_()
-                cov_step(z_dev[i * COV_BATCH:(i + 1) * COV_BATCH], r2m)
-            total = rdist.allreduce_moment_(r2m.mom2, r2m.count)     # the one collective
-            c1.record()
-            barrier()
-            ms_cov = max_over_ranks(c0.elapsed_time(c1))
-        extra['key_covariance_samples_per_s'] = COV_BATCH * K * world / (ms_cov / 1e3)
-        extra['key_covariance'] = {'layer': 8, 'batch': COV_BATCH, 'rows_accumulated': total,
-                                   'ms_per_step': ms_cov / K,
-                                   'collective': 'one all_reduce(sum) of mom2[512,512] fp32 + '
-                                                 'count after the last batch'}
-        # every rank builds a rewriter: its constructor collects C collectively (sharded z +
-        # one all-reduce) when torch.distributed is initialised; the edit itself is "replicas only"
+        del runner
+        torch.cuda.empty_cache()
         try:
-            extra['insert_loop'] = bench_insert(model, z_dev, device)
+            cov = bench_config3(model, device, world, rank, barrier, max_over_ranks)
+            extra['config3_key_covariance'] = cov
+            extra['key_covariance_samples_per_s'] = cov['samples_per_s']
         except Exception as e:  # noqa: BLE001
-            extra['insert_loop'] = {'error': '%s: %s' % (type(e).__name__, e)}
+            extra['config3_key_covariance'] = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            extra['config4_rewrite'] = bench_config4(model, device)
+        except Exception as e:  # noqa: BLE001
+            extra['config4_rewrite'] = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            extra['config5_sampling'] = bench_config5(model, device, world, barrier, max_over_ranks,
+                                                      args.sample_images)
+        except Exception as e:  # noqa: BLE001
+            extra['config5_sampling'] = {'error': '%s: %s' % (type(e).__name__, e)}
         if world == 1:
             # BASELINE.json configs[1]: fused StyledConv forward + backward (dX, dstyle, dW, dbias,
             # dnoise), every layer shape of the 256^2 generator at batch 32
             try:
-                del key_runner
                 torch.cuda.empty_cache()
                 from tools import bench_modconv
                 r = bench_modconv.main(B=BATCH, quiet=True, save=False)
@@ -440,12 +437,20 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'r1_conv_tc_summary.json')
+        # DRAM bytes per launch of the dominant kernel class: ncu (dram__bytes_read.sum +
+        # dram__bytes_write.sum) over every conv launch of one forward of THIS command, digested
+        # by tools/dram_summary.py into profiles/ (a profiler cannot run inside the timed bench)
+        traffic, traffic_note = None, None
+        prof = os.path.join(ROOT, 'profiles', 'r2_dram_per_launch.json')
         if os.path.exists(prof):
             try:
                 with open(prof) as f:
-                    traffic = json.load(f).get('dram_bytes_per_launch')
+                    dj = json.load(f)
+                ent = dj['kernels']['conv (conv_tc + upconv_fused)']
+                traffic = ent['dram_bytes_per_launch']
+                traffic_note = ('mean over the %d styled-conv launches of one forward, %s; '
+                                'algorithmic bytes per launch %.3g' % (
+                                    ent['launches'], dj['source'], ent['algorithmic_bytes_per_launch']))
             except Exception:
                 traffic = None
         achieved = (conv_flops / 1e12) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
@@ -465,8 +470,9 @@ def main():
                        'gflop_per_image': GFLOP_PER_IMG},
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'],
                          'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
-                         'traffic': traffic, 'kernel': 'rw::conv_tc_kernel<128> (all styled-conv '
-                         'launches of the timed steps)', 'kernel_launches': conv_launches,
+                         'traffic': traffic, 'traffic_source': traffic_note,
+                         'kernel': 'rw::conv_tc_kernel<128> + rw::upconv_fused_kernel (all '
+                         'styled-conv launches of the timed steps)', 'kernel_launches': conv_launches,
                          'kernel_ms_per_step': conv_ms / K,
                          'kernel_share_of_step': (conv_ms / K) / (ms_eager / K),
                          'timed_in': 'eager replay of the timed steps (%.2f ms/step); the headline '
@@ -484,6 +490,16 @@ def main():
             'clocks': clocks,
             'extra': extra,
         }
+        if cov is not None and 'samples_per_s' in cov:
+            # second half of BASELINE.json's metric: key-covariance samples/s (config 3)
+            cov_tf = cov['samples_per_s'] * GFLOP_PER_COV_SAMPLE / 1e3
+            line['roofline_cov'] = {
+                'bound': 'tensor', 'achieved': cov_tf, 'peak': peaks['tflops'] * world,
+                'unit': 'TFLOP/s', 'frac': cov_tf / (peaks['tflops'] * world),
+                'flop_per_unit': '%.2f GFLOP per z: context forward to layer 8 (3.17) + 1024 x '
+                                 '512^2 second moment (0.54), SURVEY.md §8d' % GFLOP_PER_COV_SAMPLE,
+                'kernels': 'conv_tc / upconv_fused (layers 2-7) + gram_tc, whole collection '
+                           'incl. the all-reduce', 'peak_source': peaks['source']}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline_generator()
         elif world > 1:
@@ -495,26 +511,122 @@ def main():
     return 0
 
 
-def bench_insert(model, z_dev, device, niter=400):
-    """Rewrite-loop iterations/sec on a tight-paste sized key (config 4 shape: 1x512x8x9)."""
-    import copy
+def bench_config3(model, device, world, rank, barrier, max_over_ranks, repeats=3):
+    """BASELINE config 3 as stated: layer-8 key covariance C over 10 000 random z through
+    `SeqStyleGanRewriter.collect_2nd_moment` (reference ganrewrite.py:83-96, tally.py:424-443),
+    STRONG scaling: the 10 000 z are sharded over the ranks, one all-reduce of (mom2, count)
+    inside the timed region, every rank ends with the same matrix."""
     from rewriting_b200.rewrite import ganrewrite
-    zds = torch.utils.data.TensorDataset(z_dev[:16].cpu())
-    gw = ganrewrite.SeqStyleGanRewriter(copy.deepcopy(model), zds, 8)
+    from rewriting_b200.utils import zdataset
+    zds = torch.utils.data.TensorDataset(zdataset.standard_z_sample(N_COV, 512, seed=1))
+    # the constructor runs one full collection: graph capture + weight planes = warm-up
+    gw = ganrewrite.SeqStyleGanRewriter(model, zds, 8)
+    c_first = gw.c_matrix.clone()
+    times = []
+    for _ in range(repeats):
+        barrier()
+        t0 = time.perf_counter()
+        C = gw.collect_2nd_moment()
+        torch.cuda.synchronize()
+        times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    ms = sorted(times)[len(times) // 2]
+    rel = float(((C.to(device) - c_first).norm() / c_first.norm()).item())
+    return {'n_z': N_COV, 'layer': 8, 'scaling': 'strong', 'ms_total': ms,
+            'samples_per_s': N_COV / (ms / 1e3), 'ms_all_repeats': times,
+            'pass_size': gw._moment_bs, 'passes_per_rank': -(-N_COV // (gw._moment_bs * world)),
+            'repeatability_rel_fro': rel,
+            'timing': 'host clock around collect_2nd_moment() between device synchronisations '
+                      '(the call ends with C on the host), max over ranks, median of %d' % repeats,
+            'collective': 'one all_reduce(sum) of mom2[512,512] fp32 + count, inside the timing'}
+
+
+def bench_config4(model, device):
+    """BASELINE config 4 as stated: rank-1 projected-gradient rewrite on the shipped request
+    notebooks/masks/stylegan/horse/hat_on_horse_ears.json (committed copy under tests/golden/),
+    4 context keys, zds = 1000, layer 8, 2001 iterations, piter 10, lr 0.05 — through
+    `apply_edit` (key finding + insert) and the insert loop alone (ganrewrite.py:135-169, 254-298)."""
+    from rewriting_b200.rewrite import ganrewrite
+    from rewriting_b200.utils import zdataset
+    with open(os.path.join(ROOT, 'tests', 'golden', 'hat_on_horse_ears.json')) as f:
+        request = json.load(f)
+    zds = torch.utils.data.TensorDataset(zdataset.standard_z_sample(1000, 512, seed=1))
+    t0 = time.perf_counter()
+    gw = ganrewrite.SeqStyleGanRewriter(model, zds, 8)
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    W0 = gw.target_weights().detach().clone()
+
+    def restore():
+        with torch.no_grad():
+            gw.target_weights()[...] = W0
+    gw.apply_edit(request, rank=1, niter=50)                     # warm-up (graphs, caches)
+    restore()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gw.apply_edit(request, rank=1, niter=2001, piter=10, lr=0.05)
+    torch.cuda.synchronize()
+    t_edit = time.perf_counter() - t0
+    restore()
     with torch.no_grad():
-        bag = gw.context_model(gw.get_z(0))
-        tgt = gw.target_model(bag)
-        gin = type(bag)(bag, fmap=bag.fmap[:, :, 10:18, 12:21].contiguous())
-        gout = type(bag)(bag, fmap=(tgt.fmap[:, :, 10:18, 12:21] * 1.5 + 0.3).contiguous())
-        q, _ = torch.linalg.qr(torch.randn(512, 1, device=device))
-        d = q.t().contiguous()
-    gw.insert(gin, gout, d, niter=20)                         # warm-up
-    ms = gw.insert(gin, gout, d, niter=niter, return_timing=True)
-    bytes_per_iter = 6 * 512 * 512 * 9 * 4
-    return {'its_per_s': niter / (ms / 1e3), 'ms_total': ms, 'niter': niter,
-            'key_crop': [1, 512, 8, 9], 'rank': 1,
-            'algorithmic_GBps': bytes_per_iter * niter / (ms / 1e3) / 1e9,
-            'note': 'one rw_insert_loop launch for all iterations; W,m,v stay in smem/L2'}
+        obj_acts, _, obj_area, _ = gw.object_from_selection(*request['object'])
+        goal_in, goal_out, _, _ = gw.paste_from_selection(request['paste'][0], request['paste'][1],
+                                                          obj_acts, obj_area)
+        d = gw.multi_key_from_selection(request['key'], rank=1)
+    losses = []
+    ms = gw.insert(goal_in, goal_out, d, niter=2001, piter=10, lr=0.05, return_timing=True)
+    restore()
+    gw.insert(goal_in, goal_out, d, niter=2001, piter=10, lr=0.05,
+              update_callback=lambda it, loss: losses.append(loss))
+    restore()
+    crop = list(goal_in.fmap.shape)
+    Cout, Cin = W0.shape[1], W0.shape[2]
+    P = crop[0] * crop[2] * crop[3]
+    flop_it = 2.0 * 2 * P * Cout * Cin * 9            # forward conv on the crop + weight gradient
+    state_bytes = 6 * Cout * Cin * 9 * 4              # W, m, v read + written if they streamed from HBM
+    key_bytes = 2 * (Cout // 4) * crop[0] * (crop[2] + 2) * (crop[3] + 2) * Cin * 4
+    its = 2001 / (ms / 1e3)
+    return {'request': 'hat_on_horse_ears.json (object 441, paste 854, keys 354/956/309/926)',
+            'niter': 2001, 'rank': 1, 'key_crop': crop, 'rewriter_init_s_1000z': t_init,
+            'apply_edit_s': t_edit, 'apply_edit_its_per_s': 2001 / t_edit,
+            'insert_ms': ms, 'insert_its_per_s': its,
+            'final_loss': float(losses[-1]), 'first_loss': float(losses[0]),
+            'roofline': {
+                'bound': 'latency (neither L2 nor HBM bandwidth)',
+                'l2_key_traffic_GBps': key_bytes * its / 1e9,
+                'fp32_TFLOPs': flop_it * its / 1e12,
+                'hbm_equivalent_GBps_if_state_streamed': state_bytes * its / 1e9,
+                'note': 'W[o] lives in shared memory for all iterations, m/v stream through L2; '
+                        'the key crop is re-read from L2 by every 4-channel CTA twice per iteration. '
+                        'ncu (profiles/r2_ncu_insert_before_details.txt): DRAM 0.03 %, L2 3.8 %, L2 hit '
+                        '99.4 %, issue slots 46 %, 8 warps/SM at 255 registers: latency-bound '
+                        '(stall_wait / long_scoreboard on the L2 key loads), 128 of 148 SMs busy '
+                        '(512 output channels / 4 per CTA)'}}
+
+
+def bench_config5(model, device, world, barrier, max_over_ranks, nimgs):
+    """BASELINE config 5: 50 000-sample generation (the reference generates 50 010:
+    utils/get_samples.py:114-129), reference batches of 10 with seed 10*j sharded over the ranks,
+    uint8 NHWC written by the last ToRGB combine, pipelined D2H into pinned host memory."""
+    if nimgs <= 0:
+        return {'skipped': True}
+    from rewriting_b200 import sampling
+    seen = {'n': 0, 'sum': 0}
+
+    def sink(images, batches):
+        seen['n'] += images.shape[0]
+        seen['sum'] += int(images[0, 0, 0, 0])            # touch the landed data
+    sampling.get_samples(model, nimgs=640 * world, out_dtype=torch.uint8, group=4,
+                         sink=lambda im, b: None)              # warm-up: capture + pinned ring
+    barrier()
+    t0 = time.perf_counter()
+    _, mine = sampling.get_samples(model, nimgs=nimgs, out_dtype=torch.uint8, group=4, sink=sink)
+    torch.cuda.synchronize()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    total = (nimgs // 10 + 1) * 10
+    return {'images': total, 'ms_total': ms, 'images_per_s': total / (ms / 1e3),
+            'this_rank_images': seen['n'], 'images_per_replay': 40, 'out': 'uint8 NHWC on the host',
+            'd2h_bytes': total * SIZE * SIZE * 3, 'scaling': 'strong',
+            'timing': 'host clock around get_samples() incl. z generation, H2D, D2H; max over ranks'}
 
 
 if __name__ == '__main__':

@@ -255,6 +255,21 @@ typedef struct rw_insert_args {
 } rw_insert_args;
 int rw_insert_loop(const rw_insert_args* args, rw_stream_t stream);
 
+/* ---- ProgGAN generator leaves (reference utils/proggan.py:128-181): the target of
+ * ProgressiveGanRewriter is a plain `layerN.conv` (ganrewrite.py:25-96) ----
+ * rw_pixel_norm_nchw: PixelNormLayer, x / sqrt(mean_c x^2 + 1e-8), optionally fused with the
+ *   following DoubleResolutionLayer (nearest 2x, up2 = 1: out is [B,C,2H,2W]);
+ * rw_nearest_up2: DoubleResolutionLayer alone on [planes,H,W];
+ * rw_conv3x3_bias_act: 3x3 conv (pad 1) over key planes on the tensor-core row-GEMM with
+ *   + bias[o] and leaky-ReLU(0.2) * act_gain in the epilogue — NormConvBlock's conv -> WScaleLayer
+ *   -> LeakyReLU when the WScale factor is folded into the weight planes (rw_prep_weights scale). */
+int rw_pixel_norm_nchw(const float* x, int B, int C, int H, int W, int up2, float* out,
+                       rw_stream_t stream);
+int rw_nearest_up2(const float* x, long long planes, int H, int W, float* out, rw_stream_t stream);
+int rw_conv3x3_bias_act(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                        const float* bias, int act, float act_gain, int B, int Cin, int Cout, int H,
+                        int W, float* out, rw_stream_t stream);
+
 /* ---- bring-up hooks (tests/tools only) ---- */
 /* rw_modconv_up_fused with demod = next_scale = ones_bo, additionally dumping the raw tap products
  * P[b][y][x][tap][Cout] of the tensor-core stage */

@@ -42,8 +42,32 @@ def lam_of(W, W0, d):
     return torch.einsum('goiyx,i->goyx', (W - W0).double(), d[0].double())[0]
 
 
+def c64_anchor(n=200):
+    """tests/golden/c64_200z.npz: E[kk^T] over the first `n` z with the oracle's keys accumulated
+    in float64.  The reference accumulates `mom2` in fp32 (runningstats.py:1086-1097): measured
+    here, its own rounding error grows to 1.4e-5 rel-Frobenius after 200 z and ~1.5e-4 after the
+    1000 z of config 4 — the reference's C is a looser target than the exact statistic."""
+    from rewriting_b200.synthetic import seeded_generator
+    from rewriting_b200.utils import zdataset
+    sd = seeded_generator().state_dict()
+    z = zdataset.standard_z_sample(1000, 512, seed=1)
+    acc = torch.zeros(512, 512, dtype=torch.float64)
+    rows = 0
+    for j in range(n // 10):
+        with torch.no_grad():
+            k = orc.generator_forward(sd, z[10 * j:10 * j + 10], upto_key_layer=8)
+        f = k.permute(0, 2, 3, 1).reshape(-1, 512).double()
+        acc += f.t() @ f
+        rows += f.shape[0]
+    np.savez_compressed(os.path.join(GOLD, 'c64_200z.npz'), n_z=n, count=rows,
+                        C64=(acc / rows).numpy().astype(np.float32))
+    print('wrote c64_200z.npz (%d rows)' % rows)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if '--c64-only' in sys.argv:
+        return c64_anchor()
     ref = load_reference()
     ref_model = orc.seeded_state_dict(
         lambda: ref.models.SeqStyleGAN2(256, style_dim=512, n_mlp=8, mconv='seq')).eval()
@@ -120,6 +144,7 @@ def main():
         max_abs_dW_2001=dW.abs().max().item(),
     )
     print('wrote', os.path.join(GOLD, 'config4_hat.npz'))
+    c64_anchor()
 
 
 if __name__ == '__main__':

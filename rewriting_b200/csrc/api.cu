@@ -316,6 +316,40 @@ static int fill_conv3x3(ConvTcParams& p, int B, int Cin, int Cout, int H, int W)
   return RW_OK;
 }
 
+int rw_conv3x3_bias_act(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                        const float* bias, int act, float act_gain, int B, int Cin, int Cout, int H,
+                        int W, float* out, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !out || B < 1) {
+    set_last_error("rw_conv3x3_bias_act: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  ConvTcParams p;
+  int rc = fill_conv3x3(p, B, Cin, Cout, H, W);
+  if (rc) return rc;
+  p.bias = bias;
+  p.act = act;
+  p.act_gain = act_gain;
+  p.out = out;
+  return conv_tc_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, 9 * Cin, stream);
+}
+
+int rw_pixel_norm_nchw(const float* x, int B, int C, int H, int W, int up2, float* out,
+                       rw_stream_t stream) {
+  if (!x || !out) {
+    set_last_error("rw_pixel_norm_nchw: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return pixel_norm_nchw_launch(x, B, C, H, W, up2, out, stream);
+}
+
+int rw_nearest_up2(const float* x, long long planes, int H, int W, float* out, rw_stream_t stream) {
+  if (!x || !out) {
+    set_last_error("rw_nearest_up2: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  return nearest_up2_launch(x, planes, H, W, out, stream);
+}
+
 int rw_modconv_fwd_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi,
                          const void* wt_lo, const float* scale_bo, const float* noise,
                          long long noise_bstride, const float* noise_w, const float* bias, int act,

@@ -332,6 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                         static_cast<size_t>(yy) * Wv + xx);
         float* outp = p.out + p.ph_out_ofs[ph] + static_cast<size_t>(b) * p.out_sb +
                       static_cast<size_t>(yy) * p.out_sy + static_cast<size_t>(xx) * p.out_sx;
+        const float act_gain = p.act_gain != 0.f ? p.act_gain : 1.4142135623730951f;
         const float* rw0 = p.rgb_w ? p.rgb_w + (static_cast<size_t>(b) * 3) * p.Cout : nullptr;
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
@@ -341,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           if (scl) t *= __ldg(scl + o);
           t += nz;
           if (p.bias) t += __ldg(p.bias + o);
-          if (p.act) t = (t > 0.f ? t : 0.2f * t) * 1.4142135623730951f;
+          if (p.act) t = (t > 0.f ? t : 0.2f * t) * act_gain;
           acc[j] = t;
           if (p.out != nullptr && p.out_mode == 0) outp[static_cast<size_t>(o) * p.out_sc] = t;
           if (rw0) {

@@ -34,7 +34,8 @@ struct ConvTcParams {
   const float* noise;     // [B, noise_bstride] or null, indexed y*Wv + x
   long long noise_bstride;
   const float* noise_w;   // device scalar (read by the kernel: no host sync per layer)
-  int act;                // 1 -> leaky_relu(0.2) * sqrt(2)
+  int act;                // 1 -> leaky_relu(0.2) * act_gain
+  float act_gain;         // 0 -> sqrt(2) (FusedLeakyReLU); ProgGAN's nn.LeakyReLU uses 1
   float* out;             // may be null when only planes / rgb partials are wanted
   long long out_sb, out_sc, out_sy, out_sx;  // element strides: batch, channel, y, x
   // out_mode 0: strided (NCHW-like) store at valid positions only
@@ -131,6 +132,10 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
                   int act, int n, const float* const* w, const float* const* bias,
                   float* const* out, const int* lat, const int* chans, cudaStream_t stream);
 int pixel_norm_launch(const float* z, int B, int K, float* out, cudaStream_t stream);
+int pixel_norm_nchw_launch(const float* x, int B, int C, int H, int W, int up2, float* out,
+                           cudaStream_t stream);
+int nearest_up2_launch(const float* x, long long planes, int H, int W, float* out,
+                       cudaStream_t stream);
 int demod_multi_launch(int B, float eps, int n, const float* const* style,
                        const float* const* wsq, float* const* out, const int* cout,
                        const int* cin, const int* kind, const float* wscale,

@@ -1055,6 +1055,61 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// ProgGAN leaves (reference utils/proggan.py:128-141): PixelNormLayer
+//   out[b,c,y,x] = x[b,c,y,x] / sqrt(mean_c x[b,:,y,x]^2 + 1e-8)
+// optionally fused with the following DoubleResolutionLayer (nearest 2x): every normalised value
+// is stored to its 2 x 2 output pixels.  One thread per input pixel, coalesced along x for every
+// channel plane; two passes over the C values of the pixel (the second one hits L1/L2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pixel_norm_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W, int up2,
+                       float* __restrict__ out) {
+  const long long hw = static_cast<long long>(H) * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * hw) return;
+  const int b = static_cast<int>(idx / hw);
+  const long long pix = idx - static_cast<long long>(b) * hw;
+  const float* src = x + static_cast<long long>(b) * C * hw + pix;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(src + c * hw);
+    ss = fmaf(v, v, ss);
+  }
+  // x / sqrt(mean + eps): a true division like the reference (not x * rsqrt)
+  const float den = sqrtf(ss / static_cast<float>(C) + 1e-8f);
+  if (!up2) {
+    float* dst = out + static_cast<long long>(b) * C * hw + pix;
+    for (int c = 0; c < C; ++c) dst[c * hw] = __ldg(src + c * hw) / den;
+  } else {
+    const int y = static_cast<int>(pix / W), xx = static_cast<int>(pix - static_cast<long long>(y) * W);
+    const long long hw2 = 4 * hw;
+    float* dst = out + static_cast<long long>(b) * C * hw2 + (2LL * y) * (2 * W) + 2 * xx;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(src + c * hw) / den;
+      float* d = dst + c * hw2;
+      *reinterpret_cast<float2*>(d) = make_float2(v, v);
+      *reinterpret_cast<float2*>(d + 2 * W) = make_float2(v, v);
+    }
+  }
+}
+
+// nearest-neighbour 2x of [planes, H, W] (DoubleResolutionLayer on its own)
+__global__ void __launch_bounds__(256)
+nearest_up2_kernel(const float* __restrict__ x, long long n_in, int H, int W,
+                   float* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_in) return;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long pl = idx / hw;
+  const long long pix = idx - pl * hw;
+  const int y = static_cast<int>(pix / W), xx = static_cast<int>(pix - static_cast<long long>(y) * W);
+  const float v = __ldg(x + idx);
+  float* d = out + pl * 4 * hw + (2LL * y) * (2 * W) + 2 * xx;
+  *reinterpret_cast<float2*>(d) = make_float2(v, v);
+  *reinterpret_cast<float2*>(d + 2 * W) = make_float2(v, v);
+}
+
 inline int grid_for(long long n, int threads, int cap = 148 * 16) {
   long long g = (n + threads - 1) / threads;
   if (g > cap) g = cap;
@@ -1298,6 +1353,30 @@ int pixel_norm_launch(const float* z, int B, int K, float* out, cudaStream_t str
   const int blocks = (B * 32 + 255) / 256;
   pixel_norm_kernel<<<blocks, 256, 0, stream>>>(z, B, K, out);
   return check_cuda(cudaGetLastError(), "pixel_norm launch");
+}
+
+int pixel_norm_nchw_launch(const float* x, int B, int C, int H, int W, int up2, float* out,
+                           cudaStream_t stream) {
+  const long long n = static_cast<long long>(B) * H * W;
+  if (n <= 0 || C < 1 || (up2 && (reinterpret_cast<uintptr_t>(out) & 7u))) {
+    set_last_error("pixel_norm_nchw: bad shape / alignment");
+    return RW_ERR_BAD_ARG;
+  }
+  const long long blocks = (n + 255) / 256;
+  pixel_norm_nchw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, B, C, H, W, up2, out);
+  return check_cuda(cudaGetLastError(), "pixel_norm_nchw launch");
+}
+
+int nearest_up2_launch(const float* x, long long planes, int H, int W, float* out,
+                       cudaStream_t stream) {
+  const long long n = planes * H * W;
+  if (n <= 0 || (reinterpret_cast<uintptr_t>(out) & 7u)) {
+    set_last_error("nearest_up2: bad shape / alignment");
+    return RW_ERR_BAD_ARG;
+  }
+  const long long blocks = (n + 255) / 256;
+  nearest_up2_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, n, H, W, out);
+  return check_cuda(cudaGetLastError(), "nearest_up2 launch");
 }
 
 int demod_multi_launch(int B, float eps, int n, const float* const* style,

@@ -128,6 +128,12 @@ def forward(model, z, upto_key_layer=None, noise_period=None, out_u8=False):
     `noise_period`: sample i takes the noise row (i % noise_period) — see ops.noise_table.
     `out_u8`: return the image as NHWC uint8, clamp(x*127.5+127.5, 0, 255), written by the last
     ToRGB combine (the fp32 image is then never stored)."""
+    from .utils import nvtx
+    with nvtx.range('rw:generator' if upto_key_layer is None else 'rw:context'):
+        return _forward(model, z, upto_key_layer, noise_period, out_u8)
+
+
+def _forward(model, z, upto_key_layer, noise_period, out_u8):
     from .utils.stylegan2 import models as sg2
     layers = _layer_list(model)
     if layers is None:

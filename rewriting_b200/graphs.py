@@ -91,6 +91,11 @@ class GraphedModule(object):
         self._stage_free[i] = done
         return out
 
+    def last_copy_event(self):
+        """CUDA event recorded after the device->host copy the latest `__call__(x, out=host)`
+        issued (None if it returned device data)."""
+        return self._stage_free[self._turn ^ 1]
+
     def sync(self):
         """Wait for outstanding device->host copies issued by __call__(x, out=host)."""
         self._copy_stream.synchronize()

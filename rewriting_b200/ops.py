@@ -114,7 +114,7 @@ def split_rows(a):
 _WEIGHT_CACHE = {}
 
 
-def weight_planes(weight, kind='fwd'):
+def weight_planes(weight, kind='fwd', scale=None):
     """(hi, lo, wsq) planes of scale*W for a [1,Cout,Cin,3,3] / [Cout,Cin,3,3] tensor.
     Cached per tensor OBJECT (weak reference) and `_version`: the rewriter mutates W in
     place, which bumps `_version` and invalidates the entry; temporaries
@@ -125,12 +125,13 @@ def weight_planes(weight, kind='fwd'):
         w = w[0]
     Cout, Cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
-    key = (id(weight), kind)
+    if scale is None:                  # StyleGAN2's equalised-lr factor (models.py:315-319)
+        scale = 1.0 / math.sqrt(Cin * 9)
+    key = (id(weight), kind, float(scale))
     ent = _WEIGHT_CACHE.get(key)
     if ent is not None and ent[0]() is weight and ent[1] == weight._version:
         return ent[2]
     w = _f32c(w)
-    scale = 1.0 / math.sqrt(Cin * 9)
     hi = torch.empty((Cout * 9 * Cin,), dtype=torch.bfloat16, device=w.device)
     lo = torch.empty_like(hi)
     if kind == 'fwd':
@@ -138,7 +139,7 @@ def weight_planes(weight, kind='fwd'):
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 0, 0, _p(hi), _p(lo), _p(wsq),
                    _stream())
     elif kind == 'upf':        # [Cout/16][tap][16][Cin]: N = 144 tiles of the fused up-conv
-        wsq = weight_planes(weight, 'fwd')[2]
+        wsq = weight_planes(weight, 'fwd', scale)[2]
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 2, 0, _p(hi), _p(lo), None,
                    _stream())
     elif kind == 'dgrad':      # [Cin][flipped tap][Cout]
@@ -483,3 +484,80 @@ def styled_conv(x, style, weight, noise_weight=None, bias=None, upsample=False, 
     return StyledConvFunction.apply(x, style, weight, noise_weight, bias, upsample, blur_kernel,
                                     demodulate, with_noise, with_act, pre_modulated,
                                     _WeightHolder(weight))
+
+
+# --------------------------------------------------------------------------- ProgGAN leaves
+def pixel_norm_nchw(x, up2=False):
+    """PixelNormLayer (reference utils/proggan.py:128-134), optionally fused with the nearest 2x
+    of the DoubleResolutionLayer that follows it in NormUpscaleConvBlock (:137-141)."""
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, 2 * H, 2 * W) if up2 else (B, C, H, W), dtype=torch.float32,
+                      device=x.device)
+    _cabi.call('rw_pixel_norm_nchw', _p(x), B, C, H, W, 1 if up2 else 0, _p(out), _stream())
+    return out
+
+
+def nearest_up2(x):
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    _cabi.call('rw_nearest_up2', _p(x), B * C, H, W, _p(out), _stream())
+    return out
+
+
+def plain_conv_eligible(weight):
+    return (weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and
+            weight.shape[0] % 128 == 0 and weight.shape[1] % 64 == 0)
+
+
+def conv3x3_bias_act(x, weight, wscale=1.0, bias=None, act=False, act_gain=1.0):
+    """lrelu(conv3x3(x, wscale * W) + bias) on the tensor-core row-GEMM, no autograd: the fused
+    NormConvBlock tail conv -> WScaleLayer -> LeakyReLU (proggan.py:158-181)."""
+    planes, _ = prep_keys(x, None)
+    w_hi, w_lo, _ = weight_planes(weight, 'fwd', scale=wscale)
+    B, Cin, H, W = planes.B, planes.C, planes.H, planes.W
+    Cout = weight.shape[0]
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=planes.hi.device)
+    _cabi.call('rw_conv3x3_bias_act', _p(planes.hi), _p(planes.lo), _p(w_hi), _p(w_lo),
+               _p(_f32c(bias.detach()) if bias is not None else None), 1 if act else 0,
+               float(act_gain), B, Cin, Cout, H, W, _p(out), _stream())
+    return out
+
+
+class PlainConvFunction(torch.autograd.Function):
+    """y = conv3x3(x, W) (pad 1, no bias) — the `layerN.conv` target of ProgressiveGanRewriter —
+    forward and backward on the same tensor-core kernels as the styled conv (row-GEMM for y and
+    dX, col-GEMM for dW), weight scale 1."""
+
+    @staticmethod
+    def forward(ctx, x, weight, wholder):
+        x = _f32c(x)
+        planes, _ = prep_keys(x, None)
+        w_hi, w_lo, _ = weight_planes(wholder.weight, 'fwd', scale=1.0)
+        y = conv3x3_planes(planes, w_hi, w_lo, weight.shape[0])
+        ctx.save_for_backward(weight)
+        ctx.planes = planes if any(ctx.needs_input_grad) else None
+        ctx.wholder = wholder
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (weight,) = ctx.saved_tensors
+        need_x, need_w = ctx.needs_input_grad[:2]
+        g_planes, _ = prep_keys(_f32c(gy), None)
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        gx = gW = None
+        if need_x:
+            wd_hi, wd_lo, _ = weight_planes(ctx.wholder.weight, 'dgrad', scale=1.0)
+            gx = conv3x3_planes(g_planes, wd_hi, wd_lo, Cin)
+        if need_w:
+            dwt = conv_wgrad_planes(g_planes, ctx.planes)            # [Cout, 9, Cin]
+            gW = torch.empty(weight.shape, dtype=torch.float32, device=gy.device)
+            _cabi.call('rw_wgrad_finish', _p(dwt), _p(_f32c(weight.detach())), None, None, None,
+                       g_planes.B, Cout, Cin, 1.0, _p(gW), _stream())
+        return gx, gW, None
+
+
+def plain_conv(x, weight):
+    return PlainConvFunction.apply(x, weight, _WeightHolder(weight))

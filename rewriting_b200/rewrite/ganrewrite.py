@@ -34,7 +34,7 @@ import time
 import torch
 
 from .. import _cabi, ops
-from ..utils import imgviz, nethook, pbar, renormalize, tally
+from ..utils import imgviz, nethook, nvtx, pbar, renormalize, tally
 from ..utils.stylegan2 import models as sg2
 
 # module-level debugging handles the reference exposes (ganrewrite.py:13-14)
@@ -126,7 +126,12 @@ class ProgressiveGanRewriter(object):
         return new_acts
 
     def sample_image_from_latent(self, z):
-        return self.rendering_model(self.target_model(self.context_model(z)))
+        with nvtx.range('rw:context'):
+            k = self.context_model(z)
+        with nvtx.range('rw:target'):
+            v = self.target_model(k)
+        with nvtx.range('rw:rendering'):
+            return self.rendering_model(v)
 
     def target_weights(self):
         return [p for n, p in self.target_model.named_parameters() if 'weight' in n][0]
@@ -201,7 +206,7 @@ class ProgressiveGanRewriter(object):
                 per_rank = -(-per_rank // t) * t           # whole reference batches per pass
                 batch_size = max(t, min(self.FAST_MOMENT_BATCH, per_rank))
         self._moment_bs = batch_size
-        with torch.no_grad(), pbar.quiet():
+        with torch.no_grad(), pbar.quiet(), nvtx.range('rw:collect_2nd_moment'):
             if R > 1:
                 r2m = rdist.sharded_second_moment(self._key_planes, self.zds,
                                                   batch_size=batch_size,
@@ -321,10 +326,11 @@ class ProgressiveGanRewriter(object):
             t0 = time.time()
         key, val = [self.detach(d) for d in [key, val]]
         plan = self._fused_plan(key, val, context) if self.fused_insert else None
-        if plan is not None:
-            self._insert_fused(plan, key, val, context, update_callback, niter, piter, lr)
-        else:
-            self._insert_autograd(key, val, context, update_callback, niter, piter, lr)
+        with nvtx.range('rw:insert'):
+            if plan is not None:
+                self._insert_fused(plan, key, val, context, update_callback, niter, piter, lr)
+            else:
+                self._insert_autograd(key, val, context, update_callback, niter, piter, lr)
         if return_timing:
             torch.cuda.synchronize()
             return (time.time() - t0) * 1000
@@ -352,30 +358,48 @@ class ProgressiveGanRewriter(object):
 
     # -- fused path ------------------------------------------------------------------------
     def _fused_plan(self, key, val, context):
-        """Returns (dconv, noise_module, act_module) if the target model is the canonical
-        [dconv (, noise, activate)] chain on a small key, else None."""
-        if context is None or not isinstance(key, dict) or 'fmap' not in key or 'style' not in key:
+        """Returns (conv, noise_module, act_module, plain) if the target model is the canonical
+        [dconv (, noise, activate)] chain of a SeqStyleGAN2 layer — or the single plain
+        `layerN.conv` of a ProgGAN generator (plain = True) — on a small key, else None."""
+        if context is None:
             return None
-        leaves = [m for m in self.target_model.modules() if len(list(m.children())) == 0]
         if any('forward' in m.__dict__ for m in self.target_model.modules()):
             return None
-        if len(leaves) == 3:
-            dconv, nz, act = leaves
-            if not (isinstance(nz, sg2.NoiseInjectionF) and isinstance(act, sg2.FusedLeakyReLUF)):
+        leaves = [m for m in self.target_model.modules() if len(list(m.children())) == 0]
+        plain = False
+        if isinstance(key, dict):
+            if 'fmap' not in key or 'style' not in key:
                 return None
-            if abs(act.negative_slope - 0.2) > 0 or abs(act.scale - 2 ** 0.5) > 1e-12:
+            if len(leaves) == 3:
+                dconv, nz, act = leaves
+                if not (isinstance(nz, sg2.NoiseInjectionF) and isinstance(act, sg2.FusedLeakyReLUF)):
+                    return None
+                if abs(act.negative_slope - 0.2) > 0 or abs(act.scale - 2 ** 0.5) > 1e-12:
+                    return None
+            elif len(leaves) == 1:
+                dconv, nz, act = leaves[0], None, None
+            else:
                 return None
-        elif len(leaves) == 1:
-            dconv, nz, act = leaves[0], None, None
+            if not isinstance(dconv, sg2.DemodulatedConv2dF):
+                return None
+            if dconv.upsample or not dconv.demodulate or dconv.kernel_size != 3:
+                return None
+            if key.get('noise', None) is not None:
+                return None
+            k = key.fmap
+            cout = dconv.out_channel
+        elif isinstance(key, torch.Tensor):
+            # ProgressiveGanRewriter on a ProgGAN: target = `layerN.conv`, a bias-free 3x3 conv
+            if len(leaves) != 1 or not isinstance(leaves[0], torch.nn.Conv2d):
+                return None
+            dconv, nz, act, plain = leaves[0], None, None, True
+            if (dconv.kernel_size != (3, 3) or dconv.padding != (1, 1) or dconv.stride != (1, 1) or
+                    dconv.bias is not None or dconv.groups != 1 or dconv.dilation != (1, 1)):
+                return None
+            k = key
+            cout = dconv.out_channels
         else:
             return None
-        if not isinstance(dconv, sg2.DemodulatedConv2dF):
-            return None
-        if dconv.upsample or not dconv.demodulate or dconv.kernel_size != 3:
-            return None
-        if key.get('noise', None) is not None:
-            return None
-        k = key.fmap
         if not k.is_cuda or k.dtype != torch.float32:
             return None
         B, Cin, h, w = k.shape
@@ -385,27 +409,26 @@ class ProgressiveGanRewriter(object):
         # 4 gradient rows + 8 crop-sized vectors + small tables, within 225 KB
         if (8 * Cin * 9 + 8 * B * h * w + 1440) * 4 > 225 * 1024:
             return None
-        if tuple(self.target_acts(val).shape) != (B, dconv.out_channel, h, w):
+        if tuple(self.target_acts(val).shape) != (B, cout, h, w):
             return None
-        return dconv, nz, act
+        return dconv, nz, act, plain
 
     def _insert_fused(self, plan, key, val, context, update_callback, niter, piter, lr):
-        dconv, nz, act = plan
+        dconv, nz, act, plain = plan
         weight = self.target_weights()
         assert weight is dconv.weight
-        k = key.fmap
+        k = key if plain else key.fmap
         B, Cin, h, w = k.shape
-        Cout = dconv.out_channel
+        Cout = weight.shape[-4]
         dev = k.device
         with torch.no_grad():
             d = context.detach().to(dev, torch.float32).contiguous()
-            project = self.low_rank_insert or self.low_rank_gradient
             ortho = (projected_conv(weight, d, base=weight, sign=-1.0).contiguous()
                      if self.low_rank_insert else None)
             m = torch.zeros_like(weight)
             v = torch.zeros_like(weight)
             key_cl = torch.nn.functional.pad(k, (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous()
-            style = key.style.detach().to(torch.float32).contiguous()
+            style = None if plain else key.style.detach().to(torch.float32).contiguous()
             target = self.target_acts(val).detach().to(torch.float32).contiguous()
             noise = ops.noise_table(B, h * w, dev) if nz is not None else None
             bias = act.bias.detach().contiguous() if act is not None else None
@@ -419,24 +442,25 @@ class ProgressiveGanRewriter(object):
             args.W, args.m, args.v = wdata.data_ptr(), m.data_ptr(), v.data_ptr()
             args.w_ortho = ortho.data_ptr() if ortho is not None else None
             args.d = d.data_ptr()
-            args.key_cl, args.style, args.target = key_cl.data_ptr(), style.data_ptr(), \
-                target.data_ptr()
+            args.key_cl, args.target = key_cl.data_ptr(), target.data_ptr()
+            args.style = style.data_ptr() if style is not None else None
             args.noise = noise.data_ptr() if noise is not None else None
             args.bias = bias.data_ptr() if bias is not None else None
             args.loss_out = loss_buf.data_ptr()
             args.noise_w = float(nz.weight.item()) if nz is not None else 0.0
             args.lr, args.beta1, args.beta2, args.eps = float(lr), 0.9, 0.999, 1e-8
-            # torch.optim.Adam forms (1 - beta) in Python doubles and rounds once to fp32
-            # (a kernel that derives everything from float(0.9), float(0.999) is self-consistent
-            #  and tracks torch too; mixing float betas in the bias corrections with exact 1-beta
-            #  is what drifts: 6e-6 relative in the first denominators, 4e-3 on W after 11 steps)
+            # torch.optim.Adam forms (1 - beta) and the bias corrections 1 - beta**step in Python
+            # doubles and rounds once to fp32.  (A kernel that derives everything from float(0.9),
+            # float(0.999) is self-consistent and tracks torch too; mixing float betas in the bias
+            # corrections with the exact 1-beta is what drifts: 6e-6 relative in the first
+            # denominators, 4e-3 on W after 11 steps.)
             args.one_minus_beta1, args.one_minus_beta2 = 1 - 0.9, 1 - 0.999
             args.beta1_exact, args.beta2_exact = 0.9, 0.999
             args.rank, args.B, args.Cin, args.Cout, args.h, args.w = d.shape[0], B, Cin, Cout, h, w
             args.has_noise_act = 1 if nz is not None else 0
+            args.plain_conv = 1 if plain else 0
             args.niter_total, args.piter = niter, piter
             args.project_gradient = 1 if self.low_rank_gradient else 0
-            del project
             it0 = 0
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             while it0 < niter:
@@ -467,7 +491,7 @@ class ProgressiveGanRewriter(object):
         global all_obs, all_weight, all_CinvK, all_kCinvK, e_val, e_vec, kbasis, row_dirs, q
         if key_method is None:
             key_method = self.key_method
-        with torch.no_grad():
+        with torch.no_grad(), nvtx.range('rw:multi_key_from_selection'):
             if key_method == 'zca':
                 observed = self._masked_observations(imgnum_mask_pairs)
                 sel = [(w > 0).nonzero()[:, 0] for _, _, w in observed]

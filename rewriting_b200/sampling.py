@@ -54,32 +54,51 @@ def _runner(model, z0, out_dtype, period):
     return GraphedModule(fwd, z0, parameters=model.parameters)
 
 
-def _pump(runner, passes, host, zdim):
+def _pump(runner, passes, host, zdim, sink=None):
     """Drives `runner` over `passes` (callables returning the pass's z on the CPU) with double
-    buffered pinned z staging and pipelined D2H into `host[n]`."""
+    buffered pinned z staging and pipelined D2H into `host[n % len(host)]`.  With a `sink`, the
+    host buffers are a ring: `sink(n, host_view)` is called once pass n has landed, before its
+    buffer is reused (len(host) >= 3 keeps two passes in flight)."""
     zpin = torch.empty((2,) + tuple(zdim), dtype=torch.float32).pin_memory()
     consumed = [None, None]       # event after the H2D copy that last read each pinned z slot
+    landed = []                   # (pass index, copy-done event) not yet handed to the sink
+    ring = len(host)
+
+    def drain(keep):
+        while len(landed) > keep:
+            n, ev = landed.pop(0)
+            ev.synchronize()
+            sink(n, host[n % ring])
     with torch.no_grad():
         for n, make_z in enumerate(passes):
             slot = n & 1
             if consumed[slot] is not None:
                 consumed[slot].synchronize()
             zpin[slot].copy_(make_z())
-            runner(zpin[slot], out=host[n])
+            if sink is not None:
+                drain(ring - 1)               # the buffer about to be overwritten is free again
+            runner(zpin[slot], out=host[n % ring])
+            if sink is not None:
+                landed.append((n, runner.last_copy_event()))
             consumed[slot] = torch.cuda.Event()
             consumed[slot].record()
         runner.sync()
         torch.cuda.synchronize()
+        if sink is not None:
+            drain(0)
 
 
 def get_samples(model, nimgs=50000, batch=10, out_dtype=torch.float32, shard=True,
-                reference_count=True, group=4):
+                reference_count=True, group=4, sink=None):
     """images on the CPU (pinned) — [n,3,H,W] fp32, or [n,H,W,3] uint8 for out_dtype=torch.uint8 —
     and the list of global reference-batch indices they came from.
 
     reference_count=True reproduces the reference's `nimgs // batch + 1` batches
     (50 010 images for nimgs = 50 000); False generates
-    ceil(nimgs / batch) batches.  `group` reference batches run per graph replay."""
+    ceil(nimgs / batch) batches.  `group` reference batches run per graph replay.
+    `sink(images, batch_indices)`: stream the passes to a consumer (e.g. `ImageWriter.add`)
+    through a ring of three pinned buffers instead of keeping all images in host memory
+    (50 010 uint8 images are 9.8 GB); the function then returns (None, batch indices)."""
     device = next(model.parameters()).device
     nb = nimgs // batch + 1 if reference_count else -(-nimgs // batch)
     R, r = (rdist.world_size(), rdist.rank()) if shard else (1, 0)
@@ -94,17 +113,25 @@ def get_samples(model, nimgs=50000, batch=10, out_dtype=torch.float32, shard=Tru
     z0 = torch.cat([z_for_batch(j, batch, zdepth) for j in chunks[0]]).to(device)
     runner = _runner(model, z0, out_dtype, batch)
     shape = tuple(runner.static_out.shape[1:])
-    host = torch.empty((len(mine) * batch,) + shape, dtype=out_dtype).pin_memory()
     per = group * batch
-    views = [host[n * per:(n + 1) * per] for n in range(len(full))]
-    _pump(runner, [(lambda c=c: torch.cat([z_for_batch(j, batch, zdepth) for j in c])) for c in full],
-          views, z0.shape)
+    passes = [(lambda c=c: torch.cat([z_for_batch(j, batch, zdepth) for j in c])) for c in full]
+    if sink is not None:
+        ringbuf = [torch.empty((per,) + shape, dtype=out_dtype).pin_memory() for _ in range(3)]
+        _pump(runner, passes, ringbuf, z0.shape, sink=lambda n, v: sink(v, full[n]))
+        host = None
+    else:
+        host = torch.empty((len(mine) * batch,) + shape, dtype=out_dtype).pin_memory()
+        _pump(runner, passes, [host[n * per:(n + 1) * per] for n in range(len(full))], z0.shape)
     for c in tail:                 # ragged last pass: its own (smaller) replay
         zt = torch.cat([z_for_batch(j, batch, zdepth) for j in c]).to(device)
         rt = _runner(model, zt, out_dtype, batch)
-        rt(zt, out=host[len(full) * per:])
+        dst = host[len(full) * per:] if host is not None else \
+            torch.empty((len(c) * batch,) + shape, dtype=out_dtype).pin_memory()
+        rt(zt, out=dst)
         rt.sync()
         torch.cuda.synchronize()
+        if sink is not None:
+            sink(dst, c)
     return host, mine
 
 

@@ -29,6 +29,7 @@ import numpy
 import torch
 
 from .. import ops
+from . import nvtx
 
 
 class RunningSecondMoment(object):
@@ -64,7 +65,8 @@ class RunningSecondMoment(object):
             self.mom2 = torch.zeros(hi.shape[1], hi.shape[1], dtype=torch.float32,
                                     device=hi.device)
         self.count += count
-        ops.second_moment_accum_planes(self.mom2, hi, lo)
+        with nvtx.range('rw:second_moment'):
+            ops.second_moment_accum_planes(self.mom2, hi, lo)
 
     def cpu_(self):
         self.mom2 = self.mom2.cpu()

@@ -42,13 +42,35 @@ def _lam(W, W0, d):
 
 def test_covariance_over_1000_z_matches_the_reference(gw1000, c4):
     """C = E[kk^T] collected in passes of 250 z (10-periodic noise table) vs the reference's
-    batches of 10 (ganrewrite.py:83-96, tally.py:424-443)."""
+    batches of 10 (ganrewrite.py:83-96, tally.py:424-443).  The reference adds 1000 batches into
+    an fp32 accumulator; its own rounding error against an fp64 accumulation of the same keys is
+    1.4e-5 after 200 z and grows linearly (oracle/make_golden_config4.py:c64_anchor), so the
+    bound against its 1000-z matrix is 5e-4; the exact statistic is held much tighter below."""
     C = gw1000.c_matrix.double().cpu()
     Cg = torch.from_numpy(c4['C']).double()
     rel = ((C - Cg).norm() / Cg.norm()).item()
-    assert rel < 5e-5, rel
-    np.testing.assert_allclose(C.diag().numpy(), Cg.diag().numpy(), rtol=2e-4)
+    assert rel < 5e-4, rel
+    np.testing.assert_allclose(C.diag().numpy(), Cg.diag().numpy(), rtol=5e-3)
     assert torch.equal(gw1000.c_matrix, gw1000.c_matrix.t())
+
+
+def test_covariance_vs_fp64_anchor_and_batching(seeded_model):
+    """the first 200 z against the fp64-accumulated oracle statistic: closer to the exact C than
+    the reference's own fp32 accumulator gets (1.4e-5); and the pass size (10 like the reference,
+    or 100 with the 10-periodic noise table) only changes the summation order."""
+    from rewriting_b200.rewrite import ganrewrite
+    from rewriting_b200.utils import zdataset
+    anchor = dict(np.load(os.path.join(GOLD, 'c64_200z.npz')))
+    model = copy.deepcopy(seeded_model).cuda().eval()
+    zds = torch.utils.data.TensorDataset(zdataset.standard_z_sample(200, 512, seed=1))
+    gw = ganrewrite.SeqStyleGanRewriter(model, zds, 8)
+    C64 = torch.from_numpy(anchor['C64']).double()
+    rel = ((gw.c_matrix.double().cpu() - C64).norm() / C64.norm()).item()
+    assert rel < 3e-5, rel
+    C10 = gw.collect_2nd_moment(batch_size=10).double()
+    C100 = gw.collect_2nd_moment(batch_size=100).double()
+    assert ((C10 - C100).norm() / C10.norm()).item() < 1e-5
+    assert ((C10 - gw.c_matrix.double().cpu()).norm() / C10.norm()).item() < 1e-5
 
 
 def test_goal_crops_and_direction(gw1000, c4, hat_request):

@@ -53,14 +53,21 @@ def test_fastpath_launch_sequence(dry, seeded_model):
     assert img.shape == (2, 3, 256, 256)
     assert dry.count('rw_pixel_norm') == 1 and dry.count('rw_equal_linear') == 8
     assert dry.count('rw_styles') == 1 and dry.count('rw_demod_multi') == 1
-    assert dry.count('rw_modconv_fwd_fused') == 7 and dry.count('rw_modconv_up_fwd_cl') == 6
-    assert dry.count('rw_blur_up_fused') == 6 and dry.count('rw_rgb_combine') == 7
+    # every upsampling layer is ONE launch (conv_transpose + blur + activation + next planes)
+    assert dry.count('rw_modconv_fwd_fused') == 7 and dry.count('rw_modconv_up_fused') == 6
+    assert 'rw_modconv_up_fwd_cl' not in dry and 'rw_blur_up_fused' not in dry
+    assert dry.count('rw_rgb_combine') == 7
+    del dry[:]
+    with torch.no_grad():
+        u8 = fastpath.forward(seeded_model, z, out_u8=True)
+    assert u8.shape == (2, 256, 256, 3) and u8.dtype == torch.uint8
+    assert dry.count('rw_rgb_combine') == 6 and dry.count('rw_rgb_combine_u8') == 1
     del dry[:]
     with torch.no_grad():
         planes = fastpath.forward(seeded_model, z, upto_key_layer=8)
     assert (planes.B, planes.C, planes.H, planes.W) == (2, 512, 32, 32)
     assert planes.hi.shape == (2 * 33 * 33, 512)
-    assert dry.count('rw_modconv_fwd_fused') == 3 and dry.count('rw_blur_up_fused') == 3
+    assert dry.count('rw_modconv_fwd_fused') == 3 and dry.count('rw_modconv_up_fused') == 3
     assert 'rw_rgb_combine' not in dry      # key collection skips every ToRGB
 
 

@@ -21,6 +21,16 @@ def test_seeded_weights_match_reference_checksums(seeded_sd):
         assert abs(float(v.abs().sum()) - a) <= 1e-9 * max(1.0, a), k
 
 
+def test_package_synthetic_weights_are_the_golden_weights(seeded_sd):
+    """bench.py / smoke() build their model with rewriting_b200.synthetic (nothing under oracle/
+    is imported by the product arm); it must be the model the goldens were generated with."""
+    from rewriting_b200.synthetic import seeded_generator
+    sd = seeded_generator().state_dict()
+    assert list(sd) == list(seeded_sd)
+    for k in sd:
+        assert torch.equal(sd[k], seeded_sd[k]), k
+
+
 def test_generator_pixels_match_golden(seeded_sd, z40, golden):
     rec = {}
     with torch.no_grad():
