@@ -312,7 +312,7 @@ def target_forward(k, style, weight, noise_w, bias, with_noise_act=True):
 
 def insert_loop(weight, k, style, target, noise_w, bias, d, niter, piter=10, lr=0.05,
                 low_rank_insert=True, low_rank_gradient=False, with_noise_act=True,
-                record_loss=None):
+                record_loss=None, target_fn=None):
     """ProgressiveGanRewriter.insert (ganrewrite.py:254-298) with torch autograd + Adam on CPU.
     `weight` [1,Cout,Cin,3,3] is updated in place and returned."""
     weight = weight.clone().requires_grad_(True)
@@ -320,7 +320,11 @@ def insert_loop(weight, k, style, target, noise_w, bias, d, niter, piter=10, lr=
         ortho = weight - projected_conv(weight, d)
     opt = torch.optim.Adam([weight], lr=lr)
     for it in range(niter):
-        loss = F.l1_loss(target, target_forward(k, style, weight, noise_w, bias, with_noise_act))
+        if target_fn is not None:        # other target models (odd / upsampling layers)
+            out = target_fn(weight)
+        else:
+            out = target_forward(k, style, weight, noise_w, bias, with_noise_act)
+        loss = F.l1_loss(target, out)
         opt.zero_grad()
         loss.backward()
         if low_rank_gradient:

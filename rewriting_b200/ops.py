@@ -479,6 +479,68 @@ class _WeightHolder(object):
         return weight_planes(self.weight, kind)
 
 
+class ConvTransposeLeafFunction(torch.autograd.Function):
+    """t = conv_transpose2d(k, scale*W^T, stride 2) * demod(W, style) on an already-modulated key
+    — the `dconv` LEAF of an upsampling layer when nethook has split the layer at it (the blur
+    is then the next leaf): reference DemodulatedConv2dF.forward, models.py:313-329, upsample
+    branch.  Differentiable in the weight (incl. the demodulation term) and in the key, which is
+    what the rewriter's edit of an odd layer needs (ganrewrite.py:254-298); the style enters only
+    through demod and gets no gradient here (the rewriter detaches it)."""
+
+    @staticmethod
+    def forward(ctx, k, style, weight, demodulate, wholder):
+        k = _f32c(k)
+        style = _f32c(style)
+        B, Cin, H, W = k.shape
+        Cout = weight.shape[-4]
+        planes, _ = prep_keys(k, None)
+        w_hi, w_lo, wsq = wholder.planes('fwd')
+        dm = demod_factors(style, wsq) if demodulate else None
+        out = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)
+        ctx.save_for_backward(style, weight, out, dm)
+        ctx.planes = planes if any(ctx.needs_input_grad) else None
+        ctx.wholder = wholder
+        ctx.shape = (B, Cin, Cout, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gt):
+        style, weight, out, dm = ctx.saved_tensors
+        B, Cin, Cout, H, W = ctx.shape
+        need_k, _, need_w = ctx.needs_input_grad[:3]
+        gt = _f32c(gt)
+        dev = gt.device
+        rows = B * (H + 1) * (W + 1)
+        gph_hi = torch.empty((rows, 4 * Cout), dtype=torch.bfloat16, device=dev)
+        gph_lo = torch.empty_like(gph_hi)
+        # phase planes of g_t * demod over the input-resolution padded grid
+        _cabi.call('rw_prep_phase_keys', _p(gt), _p(dm), B, Cout, H, W, _p(gph_hi), _p(gph_lo),
+                   _stream())
+        gk = gW = None
+        if need_k:
+            wd_hi, wd_lo, _ = ctx.wholder.planes('dgrad_up')
+            gk = torch.empty((B, Cin, H, W), dtype=torch.float32, device=dev)
+            _cabi.call('rw_modconv_up_dgrad', _p(gph_hi), _p(gph_lo), _p(wd_hi), _p(wd_lo), None, B,
+                       Cin, Cout, H, W, _p(gk), _stream())
+        if need_w:
+            lib = _cabi.load()
+            ws = _workspace(lib.rw_gram_workspace_bytes(Cout, Cin, rows, 9), dev)
+            dwt = torch.empty((Cout, 9, Cin), dtype=torch.float32, device=dev)
+            _cabi.call('rw_conv_up_wgrad', _p(gph_hi), _p(gph_lo), _p(ctx.planes.hi),
+                       _p(ctx.planes.lo), rows, Cout, Cin, W + 1, _p(dwt), _p(ws), ws.numel() * 4,
+                       _stream())
+            # dL/d(demod) * demod = sum_pixels g_t * t  (t is the saved, demodulated output)
+            s_dot = (gt * out).sum(dim=(2, 3)).contiguous() if dm is not None else None
+            gW = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+            _cabi.call('rw_wgrad_finish', _p(dwt), _p(_f32c(weight.detach())), _p(s_dot), _p(dm),
+                       _p(style), B, Cout, Cin, 1.0 / math.sqrt(Cin * 9), _p(gW), _stream())
+        return gk, None, gW, None, None
+
+
+def conv_transpose_leaf(k, style, weight, demodulate=True):
+    return ConvTransposeLeafFunction.apply(k, style, weight, demodulate, _WeightHolder(weight))
+
+
 def styled_conv(x, style, weight, noise_weight=None, bias=None, upsample=False, blur_kernel=None,
                 demodulate=True, with_noise=True, with_act=True, pre_modulated=False):
     return StyledConvFunction.apply(x, style, weight, noise_weight, bias, upsample, blur_kernel,

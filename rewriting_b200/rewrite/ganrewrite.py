@@ -370,13 +370,18 @@ class ProgressiveGanRewriter(object):
         if isinstance(key, dict):
             if 'fmap' not in key or 'style' not in key:
                 return None
+            if len(leaves) == 4 and isinstance(leaves[0], sg2.ApplyStyle):
+                leaves = leaves[1:]        # SeqPreStyleGanRewriter: the target starts at `adain`,
+                premod = True              # i.e. the key is un-modulated: k* = style (.) fmap
+            else:
+                premod = False
             if len(leaves) == 3:
                 dconv, nz, act = leaves
                 if not (isinstance(nz, sg2.NoiseInjectionF) and isinstance(act, sg2.FusedLeakyReLUF)):
                     return None
                 if abs(act.negative_slope - 0.2) > 0 or abs(act.scale - 2 ** 0.5) > 1e-12:
                     return None
-            elif len(leaves) == 1:
+            elif len(leaves) == 1 and not premod:
                 dconv, nz, act = leaves[0], None, None
             else:
                 return None
@@ -387,6 +392,8 @@ class ProgressiveGanRewriter(object):
             if key.get('noise', None) is not None:
                 return None
             k = key.fmap
+            if premod:
+                k = key.style.detach()[:, :, None, None] * k
             cout = dconv.out_channel
         elif isinstance(key, torch.Tensor):
             # ProgressiveGanRewriter on a ProgGAN: target = `layerN.conv`, a bias-free 3x3 conv
@@ -411,13 +418,12 @@ class ProgressiveGanRewriter(object):
             return None
         if tuple(self.target_acts(val).shape) != (B, cout, h, w):
             return None
-        return dconv, nz, act, plain
+        return dconv, nz, act, plain, k
 
     def _insert_fused(self, plan, key, val, context, update_callback, niter, piter, lr):
-        dconv, nz, act, plain = plan
+        dconv, nz, act, plain, k = plan
         weight = self.target_weights()
         assert weight is dconv.weight
-        k = key if plain else key.fmap
         B, Cin, h, w = k.shape
         Cout = weight.shape[-4]
         dev = k.device

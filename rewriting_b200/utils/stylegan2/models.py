@@ -325,10 +325,7 @@ class DemodulatedConv2dF(nn.Module):
             raise NotImplementedError('DemodulatedConv2dF: only 3x3 kernels exist in StyleGAN2')
         if self.upsample:
             # conv_transpose only; the blur is the following `blur` leaf
-            planes, _ = ops.prep_keys(d.fmap, None)
-            w_hi, w_lo, wsq = ops.weight_planes(self.weight, 'fwd')
-            dm = ops.demod_factors(d.style, wsq) if self.demodulate else None
-            out = ops.convT3x3_planes(planes, w_hi, w_lo, self.out_channel, dm)
+            out = ops.conv_transpose_leaf(d.fmap, d.style, self.weight, self.demodulate)
             return DataBag(d, fmap=out)
         out = ops.styled_conv(d.fmap, d.style, self.weight, None, None, upsample=False,
                               demodulate=self.demodulate, with_noise=False, with_act=False,
@@ -393,7 +390,14 @@ class ModulatedConv2d(nn.Module):
                                    blur_kernel=self.blur.kernel if self.upsample else None,
                                    demodulate=self.demodulate, with_noise=False, with_act=False)
         if self.kernel_size == 1 and not self.demodulate and not self.upsample:
-            # generic 1x1 (ToRGB uses the fused kernel in ToRGBF.forward instead)
+            # generic 1x1 (ToRGBF.forward calls the same kernel with its bias and skip)
+            needs_grad = torch.is_grad_enabled() and (
+                input.requires_grad or s.requires_grad or self.weight.requires_grad)
+            if self.out_channel == 3 and input.is_cuda and not needs_grad:
+                zero = torch.zeros(3, dtype=torch.float32, device=input.device)
+                return ops.torgb(input, s, self.weight.detach(), zero)
+            # differentiable / non-RGB widths: plain torch (off the rewrite path; nothing in the
+            # generator builds such a layer)
             w = (self.scale * self.weight[0, :, :, 0, 0])[None] * s[:, None, :]
             return torch.einsum('boi,bihw->bohw', w, input)
         raise NotImplementedError('ModulatedConv2d kernel_size=%d demodulate=%s' % (

@@ -190,3 +190,47 @@ def test_modconv_up_fused_vs_oracle(B, Cin, Cout, H):
     got = got[:, :Ho, :Wo].permute(0, 3, 1, 2)
     err = (got - want).abs().max().item()
     assert err < 2e-4 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H', [(5, 64, 256, 64), (3, 128, 512, 96)])
+def test_fused_conv_cta_pair_large_shapes_vs_oracle(B, Cin, Cout, H):
+    """rw_modconv_fwd_fused on shapes with more than a wave of 256-row tiles (CTA pairs,
+    `cta_group::2`, several 128-column N tiles): fp32 output, next-layer planes and ToRGB partials against
+    the oracle's DemodulatedConv2dF -> NoiseInjectionF -> FusedLeakyReLUF (models.py:313-329,
+    535-546) and ToRGB sum (models.py:639-655)."""
+    from rewriting_b200 import _cabi, ops
+    torch.manual_seed(21 + H)
+    dev = 'cuda'
+    W = H
+    x = torch.randn(B, Cin, H, W)
+    style = torch.randn(B, Cin) * 0.5 + 1
+    weight = torch.randn(1, Cout, Cin, 3, 3)
+    nw, bias = torch.tensor([0.37]), torch.randn(Cout)
+    nscale = torch.randn(B, Cout) * 0.5 + 1
+    rgb_w = torch.randn(B, 3, Cout) * 0.1
+    want = orc.target_forward(style[:, :, None, None] * x, style, weight, nw, bias, True)
+    planes, _ = ops.prep_keys(x.to(dev), style.to(dev))
+    wp = torch.nn.Parameter(weight.to(dev))
+    w_hi, w_lo, wsq = ops.weight_planes(wp, 'fwd')
+    dm = ops.demod_factors(style.to(dev), wsq)
+    noise = ops.noise_table(B, H * W, dev)
+    rows = B * (H + 1) * (W + 1)
+    out = torch.empty(B, Cout, H, W, device=dev)
+    nh = torch.full((rows, Cout), float('nan'), dtype=torch.bfloat16, device=dev)
+    nl = torch.full_like(nh, float('nan'))
+    part = torch.full((Cout // 64, B, 3, H, W), float('nan'), device=dev)
+    nw_d, bias_d, ns_d, rw_d = nw.to(dev), bias.to(dev), nscale.to(dev), rgb_w.to(dev).contiguous()
+    _cabi.call('rw_modconv_fwd_fused', ops._p(planes.hi), ops._p(planes.lo), ops._p(w_hi),
+               ops._p(w_lo), ops._p(dm), ops._p(noise), noise.stride(0), ops._p(nw_d), ops._p(bias_d),
+               1, B, Cin, Cout, H, W, ops._p(out), ops._p(ns_d), ops._p(nh), ops._p(nl), ops._p(rw_d),
+               ops._p(part), ops._stream())
+    torch.cuda.synchronize()
+    tol = 2e-4 * max(1.0, want.abs().max().item())
+    assert (out.cpu() - want).abs().max().item() < tol
+    got = (nh.float() + nl.float()).cpu().view(B, H + 1, W + 1, Cout)
+    assert torch.isfinite(got).all()
+    assert got[:, H].abs().max() == 0 and got[:, :, W].abs().max() == 0
+    ref = (want * nscale[:, :, None, None]).permute(0, 2, 3, 1)
+    assert (got[:, :H, :W] - ref).abs().max().item() < 3 * tol
+    rgb_ref = torch.einsum('bco,bohw->bchw', rgb_w, want)
+    assert (part.sum(0).cpu() - rgb_ref).abs().max().item() < 5e-4 * max(1.0, rgb_ref.abs().max().item())

@@ -10,7 +10,7 @@ T="tests/test_gpu_fastpath_kernels.py tests/test_gpu_kernels.py"
 [ -f tests/test_gpu_kernels.py ] || T="tests/test_gpu_fastpath_kernels.py"
 SEL='modconv_up_fused or rgb_combine or pixel_norm or demod_multi or second_moment or styled_conv_forward'
 for tool in memcheck racecheck; do
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 \
+  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 --report-api-errors no \
     python -m pytest $T tests/test_gpu_parity.py -q -x --timeout 1100 -p no:cacheprovider -k "$SEL" \
     > gpurun_out/r2_sanitize_$tool.log 2>&1
   echo "$tool exit $?"
