@@ -316,7 +316,8 @@ def main():
         ev0.record()
         orig_call(name, *a)
         ev1.record()
-        conv_events.append((ev0, ev1, 2.0 * a[iB] * a[iCi] * a[iCo] * 9 * a[iH] * a[iW], 1))
+        conv_events.append((ev0, ev1, 2.0 * a[iB] * a[iCi] * a[iCo] * 9 * a[iH] * a[iW],
+                            'up' if name == 'rw_modconv_up_fused' else 'conv'))
     _cabi.call = timed_call
 
     # ---- public API objects: eager module and its CUDA-graph replay -------------------------
@@ -363,9 +364,14 @@ def main():
         torch.cuda.synchronize()
         timing_on['on'] = False
         ms_eager = t0.elapsed_time(t1)
-    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in conv_events)
-    conv_flops = sum(f for _, _, f, _ in conv_events)
-    conv_launches = sum(n for _, _, _, n in conv_events)
+    # dominant kernel = conv_tc (the 3x3 styled convs); the fused upsampling kernel
+    # (conv_transpose + blur + activation in one launch) is reported next to it
+    conv_ms = sum(a.elapsed_time(b) for a, b, _, k in conv_events if k == 'conv')
+    conv_flops = sum(f for _, _, f, k in conv_events if k == 'conv')
+    conv_launches = sum(1 for _, _, _, k in conv_events if k == 'conv')
+    up_ms = sum(a.elapsed_time(b) for a, b, _, k in conv_events if k == 'up')
+    up_flops = sum(f for _, _, f, k in conv_events if k == 'up')
+    up_launches = sum(1 for _, _, _, k in conv_events if k == 'up')
     conv_events.clear()
 
     # ---- end-to-end timing through the public API with host buffers ------------------------
@@ -471,8 +477,8 @@ def main():
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'],
                          'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
                          'traffic': traffic, 'traffic_source': traffic_note,
-                         'kernel': 'rw::conv_tc_kernel<128> + rw::upconv_fused_kernel (all '
-                         'styled-conv launches of the timed steps)', 'kernel_launches': conv_launches,
+                         'kernel': 'rw::conv_tc_kernel<128> (the 3x3 styled-conv launches of the '
+                         'timed steps: layers 2,4,...,14)', 'kernel_launches': conv_launches,
                          'kernel_ms_per_step': conv_ms / K,
                          'kernel_share_of_step': (conv_ms / K) / (ms_eager / K),
                          'timed_in': 'eager replay of the timed steps (%.2f ms/step); the headline '
@@ -490,6 +496,17 @@ def main():
             'clocks': clocks,
             'extra': extra,
         }
+        if up_ms > 0:
+            up_tf = (up_flops / 1e12) / (up_ms / 1e3)
+            line['roofline_upconv'] = {
+                'bound': 'tensor', 'achieved': up_tf, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                'frac': up_tf / peaks['tflops'], 'kernel': 'rw::upconv_fused_kernel (layers 3,5,...,13: '
+                'conv_transpose + 4x4 blur + demod + noise + bias + leaky-ReLU + next-layer planes in one '
+                'launch; FLOPs counted for the conv_transpose only)', 'kernel_launches': up_launches,
+                'kernel_ms_per_step': up_ms / K,
+                'note': 'epilogue-bound (SIMT FIR + activation behind the MMAs), see DESIGN.md §6; '
+                        'the round-1 pair conv_transpose + blur kernel took the same time with 2.3x '
+                        'the DRAM traffic'}
         if cov is not None and 'samples_per_s' in cov:
             # second half of BASELINE.json's metric: key-covariance samples/s (config 3)
             cov_tf = cov['samples_per_s'] * GFLOP_PER_COV_SAMPLE / 1e3

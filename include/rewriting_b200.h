@@ -255,6 +255,12 @@ typedef struct rw_insert_args {
 } rw_insert_args;
 int rw_insert_loop(const rw_insert_args* args, rw_stream_t stream);
 
+/* out[rows][N] = A[rows][K] . W[N][K]^T on the tensor-core row-GEMM (3-term split bf16 planes from
+ * rw_split_rows; K % 64 == 0, N % 128 == 0): the key algebra between key capture and the
+ * direction d — ZCA . k and ZCA . v of ganrewrite.py:107-110, 339-374 — without a cuBLAS call */
+int rw_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int rows, int K,
+               int N, float* out, rw_stream_t stream);
+
 /* ---- ProgGAN generator leaves (reference utils/proggan.py:128-181): the target of
  * ProgressiveGanRewriter is a plain `layerN.conv` (ganrewrite.py:25-96) ----
  * rw_pixel_norm_nchw: PixelNormLayer, x / sqrt(mean_c x^2 + 1e-8), optionally fused with the
@@ -283,6 +289,16 @@ int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const
 int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                      int rows, int Cm, int Cn, int lbo_bytes, int sbo_bytes, float* out,
                      void* workspace, size_t workspace_bytes, rw_stream_t stream);
+
+/* rw_modconv_up_fused instrumented with clock64(): prof_out[grid][8 epilogue warps][6] = cycles in
+ * {wait for the MMAs, TMEM drain, combine + mailbox + barrier, neighbour exchange + horizontal FIR,
+ * vertical FIR + activation + stores} and the step count */
+int rw_debug_upconv_profile(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                            const void* wt_lo, const float* demod, const float* kernel4x4,
+                            const float* noise, long long noise_bstride, const float* noise_w,
+                            const float* bias, const float* next_scale, void* next_hi, void* next_lo,
+                            int B, int Cin, int Cout, int H, int W, long long* prof_out,
+                            rw_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -60,10 +60,13 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_int, c_int, c_p]),
     'rw_debug_upconv_taps': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p,
                                      c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
+    'rw_rowgemm': (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     'rw_pixel_norm_nchw': (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     'rw_nearest_up2': (c_int, [c_p, c_ll, c_int, c_int, c_p, c_p]),
     'rw_conv3x3_bias_act': (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_int, c_int, c_int, c_int,
                                     c_int, c_p, c_p]),
+    'rw_debug_upconv_profile': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p,
+                                        c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     'rw_blur_up_fused': (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_ll, c_p, c_p,
                                  c_int, c_p, c_p, c_p, c_p, c_p]),
     'rw_styles': (c_int, [c_p, c_int, c_int, c_int, c_f, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -414,6 +414,22 @@ int rw_debug_upconv_taps(const void* kp_hi, const void* kp_lo, const void* wt_hi
   return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
 }
 
+int rw_debug_upconv_profile(const void* kp_hi, const void* kp_lo, const void* wt_hi,
+                            const void* wt_lo, const float* demod, const float* kernel4x4,
+                            const float* noise, long long noise_bstride, const float* noise_w,
+                            const float* bias, const float* next_scale, void* next_hi, void* next_lo,
+                            int B, int Cin, int Cout, int H, int W, long long* prof_out,
+                            rw_stream_t stream) {
+  UpFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W;
+  p.demod = demod; p.bias = bias; p.noise = noise; p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w; p.k4 = kernel4x4; p.next_scale = next_scale;
+  p.next_hi = next_hi; p.next_lo = next_lo;
+  p.debug_prof = prof_out;
+  return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
+}
+
 int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const float* kernel4x4,
                      const float* noise, long long noise_bstride, const float* noise_w,
                      const float* bias, int act, const float* next_scale, void* next_hi,
@@ -778,6 +794,15 @@ int rw_debug_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const
   p.Hp = 1; p.Wp = rows; p.ph_Hv[0] = 1; p.ph_Wv[0] = rows;   // one "image" = all rows
   p.out = out; p.out_sb = 0; p.out_sc = 1; p.out_sy = 0; p.out_sx = N;  // row-major [rows][N]
   return conv_tc_launch(p, a_hi, a_lo, w_hi, w_lo, K, stream);
+}
+
+int rw_rowgemm(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int rows, int K,
+               int N, float* out, rw_stream_t stream) {
+  if (!a_hi || !a_lo || !w_hi || !w_lo || !out || rows < 1 || K % 64 != 0 || N % 128 != 0) {
+    set_last_error("rw_rowgemm: bad argument (rows=%d K=%d N=%d)", rows, K, N);
+    return RW_ERR_BAD_ARG;
+  }
+  return rw_debug_rowgemm(a_hi, a_lo, w_hi, w_lo, rows, K, N, out, stream);
 }
 
 int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,

@@ -131,6 +131,9 @@ __device__ __forceinline__ UpItem decode_item(int item, const UpFusedParams& p) 
   return it;
 }
 
+// PROF = true: bring-up variant that accumulates, per epilogue warp, the cycles spent in each phase
+// of a step (tools/debug_upconv.py prof) into p.debug_prof; the product launches PROF = false.
+template <bool PROF>
 __global__ void __launch_bounds__(kUThreads, 1)
 upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     const __grid_constant__ CUtensorMap map_a_lo,
@@ -258,6 +261,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     const float nw = __ldg(p.noise_w);
     uint32_t step = 0;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, exchange+hf, emit, steps
 
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const UpItem it = decode_item(item, p);
@@ -299,10 +303,13 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           nz0 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 2) * Wo));
           nz1 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 1) * Wo));
         }
+        long long tq[6];
+        if constexpr (PROF) tq[0] = clock64();
         const int as = step & 1u;
         const uint32_t aphase = (step >> 1) & 1u;
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
+        if constexpr (PROF) tq[1] = clock64();
         const uint32_t tcol = tmem_base + static_cast<uint32_t>(as * kUAccStride + h * 8) +
                               (static_cast<uint32_t>(q * 32) << 16);
         float P[9][8];
@@ -312,6 +319,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+        if constexpr (PROF) tq[2] = clock64();
         if (p.debug_p != nullptr && img_ok && y < p.H && y >= it.y_emit - 1) {
           float* dp = p.debug_p + ((static_cast<size_t>(b) * p.H + y) * W + x) * 9 * p.Cout + c0;
 #pragma unroll
@@ -361,6 +369,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
           named_bar_sync(1 + h, 128);
         }
+        if constexpr (PROF) tq[3] = clock64();
         // neighbour pieces: left (ro, od) of lane x-1, right (le, od) of lane x+1
         float l_ro[2][8], l_od[2][8], r_le[2][8], r_od[2][8];
 #pragma unroll
@@ -406,6 +415,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             hf[r][1][j] = fmaf(kh[3], r_od[r][j], fmaf(kh[2], e1, fmaf(kh[1], o0, kh[0] * e0)));
           }
         }
+        if constexpr (PROF) tq[4] = clock64();
         if (emit) {
           // output rows Y0 = 2y-2 (t rows 2y-3..2y) and Y1 = 2y-1 (t rows 2y-2..2y+1)
 #pragma unroll
@@ -463,6 +473,12 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             }
           }
         }
+        if constexpr (PROF) {
+          tq[5] = clock64();
+#pragma unroll
+          for (int i = 0; i < 5; ++i) prof_acc[i] += tq[i + 1] - tq[i];
+          prof_acc[5] += 1;
+        }
         // slide the vertical window: rows 2y-1, 2y, 2y+1 become 2(y+1)-3 .. 2(y+1)-1
 #pragma unroll
         for (int xi = 0; xi < 2; ++xi)
@@ -472,6 +488,13 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             w1[xi][j] = hf[0][xi][j];
             w2[xi][j] = hf[1][xi][j];
           }
+      }
+    }
+    if constexpr (PROF) {
+      if (lane == 0 && p.debug_prof != nullptr) {
+        long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = prof_acc[i];
       }
     }
   }
@@ -534,16 +557,28 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
     return rc;
   if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, p.Cin, wrows, static_cast<uint64_t>(p.Cin) * 2, UBK, UN)))
     return rc;
+  const int grid = p.nitems < sms ? p.nitems : sms;
+  if (p.debug_prof != nullptr) {
+    static bool attr_p = false;
+    if (!attr_p) {
+      rc = check_cuda(cudaFuncSetAttribute(upconv_fused_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemTotal),
+                      "upconv_fused smem attr");
+      if (rc) return rc;
+      attr_p = true;
+    }
+    upconv_fused_kernel<true><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    return check_cuda(cudaGetLastError(), "upconv_fused launch");
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(upconv_fused_kernel,
+    rc = check_cuda(cudaFuncSetAttribute(upconv_fused_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemTotal),
                     "upconv_fused smem attr");
     if (rc) return rc;
     attr_set = true;
   }
-  const int grid = p.nitems < sms ? p.nitems : sms;
-  upconv_fused_kernel<<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  upconv_fused_kernel<false><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
   return check_cuda(cudaGetLastError(), "upconv_fused launch");
 }
 

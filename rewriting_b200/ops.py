@@ -623,3 +623,17 @@ class PlainConvFunction(torch.autograd.Function):
 
 def plain_conv(x, weight):
     return PlainConvFunction.apply(x, weight, _WeightHolder(weight))
+
+
+# --------------------------------------------------------------------------- key algebra
+def rowgemm(a, w_planes):
+    """a [M, K] fp32 (CUDA) times W^T for W [N, K] given as (hi, lo) planes from split_rows:
+    out [M, N] on the tensor-core row-GEMM (no cuBLAS between key capture and d)."""
+    a = _f32c(a)
+    M, K = a.shape
+    w_hi, w_lo = w_planes
+    N = w_hi.shape[0]
+    a_hi, a_lo = split_rows(a)
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _cabi.call('rw_rowgemm', _p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), M, K, N, _p(out), _stream())
+    return out

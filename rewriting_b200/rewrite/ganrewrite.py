@@ -228,9 +228,21 @@ class ProgressiveGanRewriter(object):
         return self.covariance_adjusted_query_key(k)
 
     def zca_whitened_query_key(self, k):
+        """ZCA . k for one key [C] or a batch [M, C] [ganrewrite.py:107-110].  CUDA batches run
+        on the tensor-core row-GEMM (`rw_rowgemm`; the bf16 hi/lo planes of the ZCA matrix are
+        cached), so no cuBLAS call sits between key capture and the direction d."""
+        zca = self.zca_matrix
+        if k.dim() == 2 and k.is_cuda and zca.is_cuda and k.dtype == torch.float32 and \
+                zca.shape[0] % 128 == 0 and zca.shape[1] % 64 == 0 and k.shape[0] > 0:
+            ent = self.__dict__.get('_zca_planes')
+            tag = (zca.data_ptr(), zca._version)
+            if ent is None or ent[0] != tag:
+                ent = (tag, ops.split_rows(zca.contiguous()))
+                self._zca_planes = ent
+            return ops.rowgemm(k, ent[1])                       # rows . ZCA^T
         if k.dim() == 1:
-            return torch.mv(self.zca_matrix, k)
-        return torch.mm(self.zca_matrix, k.permute(1, 0)).permute(1, 0)
+            return torch.mv(zca, k)
+        return torch.mm(zca, k.permute(1, 0)).permute(1, 0)
 
     # ---------------------------------------------------------------------------- requests
     def apply_edit(self, request, rank=1, niter=2001, piter=10, lr=0.05, update_callback=None,

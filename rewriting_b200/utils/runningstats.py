@@ -227,8 +227,10 @@ class RunningQuantile(object):
     for all units at once on the device (fp64 searchsorted + lerp) instead of a numpy loop per
     unit.  `r` is accepted for API compatibility and recorded as `resolution` in the state."""
 
-    def __init__(self, r=3 * 1024, buffersize=None, seed=None, state=None):
+    def __init__(self, r=3 * 1024, buffersize=None, seed=None, state=None, max_retained=1 << 22):
         if state is not None:
+            self.max_retained = max_retained
+            self._compactions = 0
             self.set_state_dict(resolve_state_dict(state))
             return
         self.resolution = r * 2
@@ -241,8 +243,17 @@ class RunningQuantile(object):
         self.batchcount = 0
         self.extremes = None
         self._chunks = []          # level 0: list of [depth, n_i] tensors, in arrival order
-        self._upper = []           # levels 1.. (only from loaded sketches): [depth, n] or None
+        self._upper = []           # levels 1.. (weight 2^level): [depth, n] or None
         self._summary = None       # cached (sorted values, normalised centre positions)
+        # Memory bound.  Every sample is kept (exact quantiles) until a level holds more than
+        # `max_retained` values per unit; then the level is sorted and every second value moves
+        # up one level with twice the weight — the compaction step of the reference's sketch
+        # (runningstats.py:269-621), done deterministically (alternating offsets) and only at
+        # this size.  Rank error per compaction <= 1 / max_retained; with the default (4 M per
+        # unit: 8 GB at 512 units) the 10 k x 1024 samples of the UI search stay exact.
+        self.max_retained = max_retained
+        self._level0_count = 0
+        self._compactions = 0
 
     def size(self):
         return self.count
@@ -279,7 +290,35 @@ class RunningQuantile(object):
         self.extremes[:, 0] = torch.minimum(self.extremes[:, 0], chunk.min(dim=1)[0])
         self.extremes[:, 1] = torch.maximum(self.extremes[:, 1], chunk.max(dim=1)[0])
         self._chunks.append(chunk)
+        self._level0_count += chunk.shape[1]
         self._summary = None
+        if self.max_retained and self._level0_count > self.max_retained:
+            self._compact(0)
+
+    def _compact(self, level):
+        """halve `level`: sort, keep every second value (offset alternates), promote them."""
+        if level == 0:
+            vals = torch.cat(self._chunks, dim=1) if len(self._chunks) > 1 else self._chunks[0]
+        else:
+            vals = self._upper[level - 1]
+        vals = torch.sort(vals, dim=1)[0]
+        n = vals.shape[1]
+        keep_here = vals[:, n - (n % 2):]             # an odd leftover stays at this level
+        off = self._compactions & 1
+        self._compactions += 1
+        promoted = vals[:, off:n - (n % 2):2].contiguous()
+        if level == 0:
+            self._chunks = [keep_here.contiguous()] if keep_here.shape[1] else []
+            self._level0_count = keep_here.shape[1]
+        else:
+            self._upper[level - 1] = keep_here.contiguous() if keep_here.shape[1] else None
+        while len(self._upper) < level + 1:
+            self._upper.append(None)
+        up = self._upper[level]
+        self._upper[level] = promoted if up is None else torch.cat([up, promoted], dim=1)
+        self._summary = None
+        if self._upper[level].shape[1] > self.max_retained:
+            self._compact(level + 1)
 
     def _levels(self):
         """[(values [depth, n], weight)] of every non-empty level."""
@@ -417,6 +456,7 @@ class RunningQuantile(object):
         self.dtype = self.extremes.dtype
         self.device = self.extremes.device
         self._summary = None
+        self._level0_count = self._chunks[0].shape[1] if self._chunks else 0
 
 
 def resolve_state_dict(s):

@@ -115,3 +115,31 @@ def test_tally_topk_and_quantile_driver_and_cache(x, tmp_path):
     assert torch.equal(rq2.quantiles([0.5]), rq.quantiles([0.5]))
     rq3 = tally.tally_quantile(lambda b: b, x[:500], batch_size=50)
     assert torch.allclose(rq3.median(), x[:500].median(dim=0)[0], atol=0.05)
+
+
+def test_running_quantile_bounded_memory_compaction():
+    """above `max_retained` values per unit a level is halved like the reference's
+    sketch (sorted, every second value promoted with twice the weight): memory stays bounded and
+    the quantiles stay within the compaction's rank error of the exact ones."""
+    import torch
+    from rewriting_b200.utils import runningstats
+    g = torch.Generator().manual_seed(3)
+    data = torch.randn(40000, 6, generator=g) * torch.tensor([1., 2., 0.5, 3., 1., 10.]) + 0.3
+    exact = runningstats.RunningQuantile(max_retained=0)
+    small = runningstats.RunningQuantile(max_retained=1024)
+    for i in range(0, 40000, 500):
+        exact.add(data[i:i + 500])
+        small.add(data[i:i + 500])
+    kept = sum(v.shape[1] for v, _ in small._levels())
+    assert kept <= 6 * 1024 and small.size() == 40000 and len(small._upper) >= 4   # ~1 K per level
+    qs = torch.tensor([0.001, 0.01, 0.1, 0.5, 0.9, 0.99, 0.999])
+    want = exact.quantiles(qs)
+    got = small.quantiles(qs)
+    # compare in rank space: where does the estimate fall in the exact distribution?
+    rank = exact.normalize(got)
+    assert (rank - qs[None, :]).abs().max().item() < 0.01
+    assert (got[:, 3] - want[:, 3]).abs().max().item() < 0.05 * 10
+    assert abs(small.mean()[5].item() - data[:, 5].mean().item()) < 0.2
+    # the bounded sketch round-trips through its state dict (plain arrays per level)
+    again = runningstats.RunningQuantile(state=small.state_dict())
+    assert torch.allclose(again.quantiles(qs), got)
