@@ -2,6 +2,7 @@
 // small host-side utilities shared by the kernel translation units.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -427,6 +428,7 @@ int rw_debug_upconv_profile(const void* kp_hi, const void* kp_lo, const void* wt
   p.noise_w = noise_w; p.k4 = kernel4x4; p.next_scale = next_scale;
   p.next_hi = next_hi; p.next_lo = next_lo;
   p.debug_prof = prof_out;
+  p.debug_nostore = getenv("RW_UP_NOSTORE") != nullptr;
   return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
 }
 

@@ -839,120 +839,6 @@ rgb_combine_kernel(const float* __restrict__ part, int nparts, long long part_st
   }
 }
 
-// ---------------------------------------------------------------------------
-// styles: every modulation EqualLinear of the generator in ONE launch.
-//   out_l[b, c] = sum_k latent[b, lat_l, k] * (W_l[c, k] * scale) + bias_l[c]
-// (EqualLinearS / ModulatedConv2d.modulation, models.py:487-511 with lr_mul = 1,
-//  activation = None).  The reference issues one tiny sgemm per layer (20 per forward).
-// one warp per (layer, output channel); the weight row is read once, coalesced.
-// ---------------------------------------------------------------------------
-struct StyleJobs {
-  const float* w[32];
-  const float* bias[32];
-  float* out[32];
-  int lat[32];
-  int chans[32];
-  int first_warp[33];
-  int n;
-};
-
-// block = (layer, group of 8*cpw channels): the B latent rows of that layer are staged in smem
-// once (float4), every warp owns cpw output channels; a channel's weight row lives in registers
-// (K <= 512: 16 per lane, loaded once with all loads in flight) and is reused for every batch
-// row, so the kernel is not a chain of dependent weight loads (measured: 24 us -> a few us per
-// mapping layer).
-__global__ void __launch_bounds__(256)
-styles_kernel(const float* __restrict__ latent, int Btotal, int bchunk, int n_latent, int K,
-              float scale, float bias_mul, int act, int cpw, const StyleJobs jobs) {
-  extern __shared__ float xs[];            // [B][K], B = this block's batch chunk (blockIdx.y)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int l = 0;
-  const int blk = blockIdx.x;
-  while (blk >= jobs.first_warp[l + 1]) ++l;          // first_warp holds BLOCK offsets here
-  const int b_begin = blockIdx.y * bchunk;
-  const int B = min(bchunk, Btotal - b_begin);
-  const float* x0 = latent + (static_cast<size_t>(b_begin) * n_latent + jobs.lat[l]) * K;
-  if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(x0) & 15u) == 0) {
-    const int kq = K >> 2;
-    float4* xs4 = reinterpret_cast<float4*>(xs);
-    for (int i = threadIdx.x; i < B * kq; i += 256) {
-      const int b = i / kq, q = i - b * kq;
-      xs4[i] = __ldg(reinterpret_cast<const float4*>(x0 + static_cast<size_t>(b) * n_latent * K) + q);
-    }
-  } else {
-    for (int i = threadIdx.x; i < B * K; i += 256) {
-      const int b = i / K, k = i - b * K;
-      xs[i] = __ldg(x0 + static_cast<size_t>(b) * n_latent * K + k);
-    }
-  }
-  __syncthreads();
-  const int C = jobs.chans[l];
-  float* out = jobs.out[l] + static_cast<size_t>(b_begin) * C;
-  const int nk = (K + 31) >> 5;
-  for (int cc = 0; cc < cpw; ++cc) {
-    const int c = ((blk - jobs.first_warp[l]) * 8 + warp) * cpw + cc;
-    if (c >= C) break;
-    const float* wrow = jobs.w[l] + static_cast<size_t>(c) * K;
-    const float bv = __ldg(jobs.bias[l] + c) * bias_mul;
-    if (nk <= 16) {
-      float wv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int k = lane + 32 * j;
-        wv[j] = (k < K) ? __ldg(wrow + k) * scale : 0.f;
-      }
-      for (int b0 = 0; b0 < B; b0 += 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* xr[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xr[i] = xs + static_cast<size_t>(min(b0 + i, B - 1)) * K;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = lane + 32 * j;
-          if (k < K) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(xr[i][k], wv[j], acc[i]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a = acc[i];
-#pragma unroll
-          for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          if (lane == 0 && b0 + i < B) {
-            float v = a + bv;
-            if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;   // fused_leaky_relu
-            out[static_cast<size_t>(b0 + i) * C + c] = v;
-          }
-        }
-      }
-    } else {                                  // long rows: stream the weights per 8-row group
-      for (int b0 = 0; b0 < B; b0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int k = lane; k < K; k += 32) {
-          const float wv = __ldg(wrow + k) * scale;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (b0 + i < B) acc[i] = fmaf(xs[(b0 + i) * K + k], wv, acc[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a = acc[i];
-#pragma unroll
-          for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          if (lane == 0 && b0 + i < B) {
-            float v = a + bv;
-            if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
-            out[static_cast<size_t>(b0 + i) * C + c] = v;
-          }
-        }
-      }
-    }
-  }
-}
-
 // z * rsqrt(mean(z^2, dim=1) + 1e-8)   (PixelNormL, models.py:609-614); one warp per row
 __global__ void pixel_norm_kernel(const float* __restrict__ z, int B, int K, float* __restrict__ out) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1051,6 +937,97 @@ demod_multi_kernel(int B, float eps, const DemodJobs jobs) {
 #pragma unroll
       for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
       if (lane == 0) out[static_cast<size_t>(b) * Cout + o] = rsqrtf(acc + eps);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small_gemm: out[b, o] = epi( sum_i f(A[b, i]) * W[o, i] ) for several (A, W, out) jobs in one
+// launch — the latent-only linears of the generator at ANY batch size:
+//   mode 0 (EqualLinear / modulation, models.py:487-533):  f = id,
+//          out = act( acc * scale + bias[o] * bias_mul )           act = leaky-ReLU(0.2) * sqrt(2)
+//   mode 1 (demodulation factor, models.py:320-328):       f = square,
+//          out = rsqrt( acc + eps )                                (W = Wsq[o, i])
+// Classic shared-memory tiling: 32 batch rows x 64 output channels per block, K chunks of 32,
+// 2 x 4 outputs per thread.  The warp-per-channel kernels it replaces re-staged the whole
+// latent batch per block (styles) or re-read every style row per output channel (demod): at the
+// 250-row passes of the covariance collection they took 0.56 ms of a 3 ms pass.
+// ---------------------------------------------------------------------------
+struct GemmJobs {
+  const float* a[32];       // [B, a_stride] rows (row b at a + b * a_stride)
+  const float* w[32];       // [N, K]
+  const float* bias[32];    // [N] or null
+  float* out[32];           // [B, N]
+  int n_out[32];
+  int first_block[33];
+  int n;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(int B, int K, long long a_stride, float scale, float bias_mul, int act, float eps,
+                  const GemmJobs jobs) {
+  __shared__ float As[32][33];
+  __shared__ float Ws[64][33];
+  int l = 0;
+  const int blk = blockIdx.x;
+  while (blk >= jobs.first_block[l + 1]) ++l;
+  const int N = jobs.n_out[l];
+  const int n0 = (blk - jobs.first_block[l]) * 64;
+  const int b0 = blockIdx.y * 32;
+  const float* A = jobs.a[l];
+  const float* Wm = jobs.w[l];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;          // 16 x 16 threads: rows 2*ty.., cols 4*tx..
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                   // A tile: 32 rows x 32 k
+      const int e = tid + 256 * i;
+      const int r = e >> 5, c = e & 31;
+      float v = 0.f;
+      if (b0 + r < B && k0 + c < K) v = __ldg(A + static_cast<size_t>(b0 + r) * a_stride + k0 + c);
+      As[r][c] = (MODE == 1) ? v * v : v;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                   // W tile: 64 rows x 32 k
+      const int e = tid + 256 * i;
+      const int r = e >> 5, c = e & 31;
+      float v = 0.f;
+      if (n0 + r < N && k0 + c < K) v = __ldg(Wm + static_cast<size_t>(n0 + r) * K + k0 + c);
+      Ws[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = As[2 * ty][kk], a1 = As[2 * ty + 1][kk];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float wv = Ws[4 * tx + c][kk];
+        acc[0][c] = fmaf(a0, wv, acc[0][c]);
+        acc[1][c] = fmaf(a1, wv, acc[1][c]);
+      }
+    }
+    __syncthreads();
+  }
+  float* out = jobs.out[l];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = b0 + 2 * ty + r;
+    if (b >= B) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int o = n0 + 4 * tx + c;
+      if (o >= N) continue;
+      float v;
+      if (MODE == 1) {
+        v = rsqrtf(acc[r][c] + eps);
+      } else {
+        v = acc[r][c] * scale;
+        if (jobs.bias[l]) v += __ldg(jobs.bias[l] + o) * bias_mul;
+        if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
+      }
+      out[static_cast<size_t>(b) * N + o] = v;
     }
   }
 }
@@ -1304,48 +1281,28 @@ int rgb_combine_launch(const float* part, int nparts, int B, int H, int W, const
 int styles_launch(const float* latent, int B, int n_latent, int K, float scale, float bias_mul,
                   int act, int n, const float* const* w, const float* const* bias,
                   float* const* out, const int* lat, const int* chans, cudaStream_t stream) {
-  // many layers in one launch: 4 channels per warp (fewer blocks re-staging the same latent rows);
-  // a single layer (mapping network): 1 channel per warp so that 64 SMs share the work
-  const int cpw = (n > 1) ? 4 : 1;
   if (n < 1 || n > 32) {
     set_last_error("styles: %d layers (max 32)", n);
     return RW_ERR_BAD_ARG;
   }
-  StyleJobs jobs;
+  // NOTE the equalised-lr convention: out = x . (W * scale)^T + bias * bias_mul; the scale is
+  // applied to the accumulated sum here (one rounding per output instead of one per weight)
+  GemmJobs jobs;
   jobs.n = n;
-  int warps = 0;
+  int blocks = 0;
   for (int i = 0; i < n; ++i) {
+    jobs.a[i] = latent + static_cast<size_t>(lat[i]) * K;
     jobs.w[i] = w[i];
     jobs.bias[i] = bias[i];
     jobs.out[i] = out[i];
-    jobs.lat[i] = lat[i];
-    jobs.chans[i] = chans[i];
-    jobs.first_warp[i] = warps;
-    warps += (chans[i] + 8 * cpw - 1) / (8 * cpw);          // blocks of 8*cpw channels
+    jobs.n_out[i] = chans[i];
+    jobs.first_block[i] = blocks;
+    blocks += (chans[i] + 63) / 64;
   }
-  jobs.first_warp[n] = warps;
-  // the latent rows of a block are staged in shared memory, and that staging (not the FMAs) is
-  // what a block spends its time on: 16-row chunks over blockIdx.y keep it at 32 KB per block
-  // (8 blocks per SM) whatever the batch size; the weight rows are re-read from L2 per chunk
-  int bchunk = B < 16 ? B : 16;
-  while (static_cast<size_t>(bchunk) * K * sizeof(float) > 128 * 1024 && bchunk > 1)
-    bchunk = (bchunk + 1) / 2;
-  const size_t smem = static_cast<size_t>(bchunk) * K * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_last_error("styles: K too large for shared memory");
-    return RW_ERR_UNSUPPORTED;
-  }
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    int rc = check_cuda(cudaFuncSetAttribute(styles_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)), "styles smem attr");
-    if (rc) return rc;
-    attr = smem;
-  }
-  dim3 grid(warps, (B + bchunk - 1) / bchunk);
-  styles_kernel<<<grid, 256, smem, stream>>>(latent, B, bchunk, n_latent, K, scale, bias_mul, act,
-                                             cpw, jobs);
+  jobs.first_block[n] = blocks;
+  dim3 grid(blocks, (B + 31) / 32);
+  small_gemm_kernel<0><<<grid, 256, 0, stream>>>(B, K, static_cast<long long>(n_latent) * K, scale,
+                                                 bias_mul, act, 0.f, jobs);
   return check_cuda(cudaGetLastError(), "styles launch");
 }
 
@@ -1387,21 +1344,51 @@ int demod_multi_launch(int B, float eps, int n, const float* const* style,
     set_last_error("demod_multi: %d jobs (max 32)", n);
     return RW_ERR_BAD_ARG;
   }
+  // kind 0 (demodulation factors): tiled GEMM over style^2, one launch per distinct Cin;
+  // kind 1 (ToRGB modulated weights): the elementwise kernel
+  for (int pass_cin = 0;;) {
+    GemmJobs g;
+    g.n = 0;
+    int blocks = 0, K = 0;                          // K = smallest Cin above pass_cin
+    for (int i = 0; i < n; ++i)
+      if (kind[i] == 0 && cin[i] > pass_cin && (K == 0 || cin[i] < K)) K = cin[i];
+    if (K == 0) break;
+    for (int i = 0; i < n; ++i) {
+      if (kind[i] != 0 || cin[i] != K) continue;
+      g.a[g.n] = style[i];
+      g.w[g.n] = wsq[i];
+      g.bias[g.n] = nullptr;
+      g.out[g.n] = out[i];
+      g.n_out[g.n] = cout[i];
+      g.first_block[g.n] = blocks;
+      blocks += (cout[i] + 63) / 64;
+      ++g.n;
+    }
+    g.first_block[g.n] = blocks;
+    dim3 grid(blocks, (B + 31) / 32);
+    small_gemm_kernel<1><<<grid, 256, 0, stream>>>(B, K, K, 1.f, 0.f, 0, eps, g);
+    int rc = check_cuda(cudaGetLastError(), "demod_multi launch");
+    if (rc) return rc;
+    pass_cin = K;
+  }
   DemodJobs jobs;
-  jobs.n = n;
+  jobs.n = 0;
   int blocks = 0;
   for (int i = 0; i < n; ++i) {
-    jobs.style[i] = style[i];
-    jobs.wsq[i] = wsq[i];
-    jobs.out[i] = out[i];
-    jobs.cout[i] = cout[i];
-    jobs.cin[i] = cin[i];
-    jobs.kind[i] = kind[i];
-    jobs.wscale[i] = wscale[i];
-    jobs.first_block[i] = blocks;
-    blocks += ((kind[i] == 1 ? B * cout[i] : cout[i] * ((B + 7) / 8)) + 7) / 8;
+    if (kind[i] != 1) continue;
+    const int j = jobs.n++;
+    jobs.style[j] = style[i];
+    jobs.wsq[j] = wsq[i];
+    jobs.out[j] = out[i];
+    jobs.cout[j] = cout[i];
+    jobs.cin[j] = cin[i];
+    jobs.kind[j] = 1;
+    jobs.wscale[j] = wscale[i];
+    jobs.first_block[j] = blocks;
+    blocks += (B * cout[i] + 7) / 8;
   }
-  jobs.first_block[n] = blocks;
+  if (jobs.n == 0) return RW_OK;
+  jobs.first_block[jobs.n] = blocks;
   demod_multi_kernel<<<blocks, 256, 0, stream>>>(B, eps, jobs);
   return check_cuda(cudaGetLastError(), "demod_multi launch");
 }

@@ -57,7 +57,8 @@ constexpr int kUBBytes = UN * UBK * 2;  // one plane of B: 18 KB
 constexpr int kUStageBytes = 2 * kUABytes + 2 * kUBBytes;    // 68 KB
 constexpr int kUAccStride = 256;        // TMEM columns between the two accumulators
 constexpr int kUMailFloats = 2 * 2 * 4 * 2 * 32;             // [buf][half][quarter][side][32]
-constexpr int kUSmemTotal = kUStages * kUStageBytes + kUMailFloats * 4 + 1024 + 256;
+constexpr int kUPairBytes = 4 * 2 * 4 * 32 * 16;               // [quarter][sender half][piece][lane][16 B]
+constexpr int kUSmemTotal = kUStages * kUStageBytes + kUMailFloats * 4 + kUPairBytes + 1024 + 256;
 
 struct UBarriers {
   uint64_t full[kUStages];
@@ -107,6 +108,48 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// vector accesses to the mailbox by 32-bit shared-window address: an edge lane moves its 32
+// values with 8 x 128-bit instructions.  (As 64 scalar loads through the generic `mail` pointer
+// inside a one-lane divergent block, this fix-up took 2 980 of a step's 7 800 cycles:
+// tools/prof_upconv.py.)
+__device__ __forceinline__ void sts_v4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
+__device__ __forceinline__ void sts_v4u(uint32_t a, const uint32_t (&w)[4]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3])
+               : "memory");
+}
+__device__ __forceinline__ void lds_v4u(uint32_t a, uint32_t (&w)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+               : "r"(a)
+               : "memory");
+}
+// one full 32-byte sector per thread (sm_100: 256-bit global store)
+__device__ __forceinline__ void stg_256(void* dst, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(a[0]),
+               "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+               : "memory");
+}
+__device__ __forceinline__ void lds_v4(uint32_t a, float& x, float& y, float& z, float& w) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+               : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
+               : "r"(a)
+               : "memory");
+}
+
+// waits of the two control warps: back off between polls — they share their schedulers with
+// epilogue warps, and ncu showed ~16 % of the kernel's issued instructions in their spin loops
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > RW_SPIN_LIMIT) __trap();
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
@@ -143,7 +186,8 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   float* mail = reinterpret_cast<float*>(smem + kUStages * kUStageBytes);
-  UBarriers* bars = reinterpret_cast<UBarriers*>(smem + kUStages * kUStageBytes + kUMailFloats * 4);
+  uint8_t* pair_area = smem + kUStages * kUStageBytes + kUMailFloats * 4;
+  UBarriers* bars = reinterpret_cast<UBarriers*>(pair_area + kUPairBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,7 +252,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       for (int y = it.y_first; y < it.y_end; ++y, ++step) {
         const int as = step & 1u;
         const uint32_t aphase = (step >> 1) & 1u;
-        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
+        mbar_wait_relaxed(&bars->tmem_empty[as], aphase ^ 1u, 32);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kUAccStride;
         for (int kb = 0; kb < kb_count; ++kb) {
@@ -261,7 +305,20 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     const float nw = __ldg(p.noise_w);
     uint32_t step = 0;
-    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, exchange+hf, emit, steps
+    // mailbox slots of this warp, as shared-window byte addresses (buffer 0; +kMailBufBytes for
+    // odd steps): slot (h, q, side) = 32 floats [row E/O][ro|le, od][8 channels]
+    constexpr uint32_t kMailBufBytes = 2 * 4 * 2 * 32 * 4;
+    const uint32_t mail_s = smem_u32(mail) + h * (4 * 2 * 32 * 4);
+    const uint32_t post_r = mail_s + (q * 2 + 1) * 128, post_l = mail_s + (q * 2 + 0) * 128;
+    const uint32_t read_l = mail_s + ((q - 1) * 2 + 1) * 128, read_r = mail_s + ((q + 1) * 2 + 0) * 128;
+    // partner exchange (the two warps of a lane quarter own 8 channels each = half of every
+    // 32-byte sector of the output planes): half 0 stores the `hi` plane, half 1 the `lo` plane;
+    // each sends the 16-byte pieces of the OTHER plane to its partner through shared memory and
+    // writes whole sectors with 256-bit stores.  [piece][lane][16 B] keeps the STS/LDS conflict-free.
+    const uint32_t pair_s = smem_u32(pair_area) + q * (2 * 4 * 32 * 16);
+    const uint32_t pair_send = pair_s + h * (4 * 32 * 16) + lane * 16;
+    const uint32_t pair_recv = pair_s + (h ^ 1) * (4 * 32 * 16) + lane * 16;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, shuffles, fixups, hf, emit, steps
 
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const UpItem it = decode_item(item, p);
@@ -303,7 +360,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           nz0 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 2) * Wo));
           nz1 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 1) * Wo));
         }
-        long long tq[6];
+        long long tq[8];
         if constexpr (PROF) tq[0] = clock64();
         const int as = step & 1u;
         const uint32_t aphase = (step >> 1) & 1u;
@@ -345,27 +402,25 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         }
         // mailbox across warp boundaries: lane 31 posts (ro, od) for its right neighbour,
         // lane 0 posts (le, od) for its left neighbour
-        float* mb = mail + ((step & 1u) * 2 + h) * (4 * 2 * 32);
+        const uint32_t mbo = (step & 1u) * kMailBufBytes;
         if (cross) {
           if (lane == 31) {
-            float* dst = mb + (q * 2 + 1) * 32;
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                dst[r * 16 + j] = ro[r][j];
-                dst[r * 16 + 8 + j] = od[r][j];
-              }
+            for (int r = 0; r < 2; ++r) {
+              sts_v4(post_r + mbo + r * 64, ro[r][0], ro[r][1], ro[r][2], ro[r][3]);
+              sts_v4(post_r + mbo + r * 64 + 16, ro[r][4], ro[r][5], ro[r][6], ro[r][7]);
+              sts_v4(post_r + mbo + r * 64 + 32, od[r][0], od[r][1], od[r][2], od[r][3]);
+              sts_v4(post_r + mbo + r * 64 + 48, od[r][4], od[r][5], od[r][6], od[r][7]);
+            }
           }
           if (lane == 0) {
-            float* dst = mb + (q * 2 + 0) * 32;
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                dst[r * 16 + j] = le[r][j];
-                dst[r * 16 + 8 + j] = od[r][j];
-              }
+            for (int r = 0; r < 2; ++r) {
+              sts_v4(post_l + mbo + r * 64, le[r][0], le[r][1], le[r][2], le[r][3]);
+              sts_v4(post_l + mbo + r * 64 + 16, le[r][4], le[r][5], le[r][6], le[r][7]);
+              sts_v4(post_l + mbo + r * 64 + 32, od[r][0], od[r][1], od[r][2], od[r][3]);
+              sts_v4(post_l + mbo + r * 64 + 48, od[r][4], od[r][5], od[r][6], od[r][7]);
+            }
           }
           named_bar_sync(1 + h, 128);
         }
@@ -381,28 +436,36 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             r_le[r][j] = __shfl_down_sync(0xffffffffu, le[r][j], 1);
             r_od[r][j] = __shfl_down_sync(0xffffffffu, od[r][j], 1);
           }
-        if (lane == 0 || first_x) {               // image edge, or a neighbour in another warp
-          const bool from_mail = cross && !first_x;
-          const float* src = mb + ((q - 1) * 2 + 1) * 32;
+        if constexpr (PROF) tq[6] = clock64();
+        if (first_x) {                            // image edge: nothing to the left
 #pragma unroll
           for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              l_ro[r][j] = from_mail ? src[r * 16 + j] : 0.f;
-              l_od[r][j] = from_mail ? src[r * 16 + 8 + j] : 0.f;
-            }
+            for (int j = 0; j < 8; ++j) l_ro[r][j] = l_od[r][j] = 0.f;
+        } else if (cross && lane == 0) {          // left neighbour lives in the previous warp
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            lds_v4(read_l + mbo + r * 64, l_ro[r][0], l_ro[r][1], l_ro[r][2], l_ro[r][3]);
+            lds_v4(read_l + mbo + r * 64 + 16, l_ro[r][4], l_ro[r][5], l_ro[r][6], l_ro[r][7]);
+            lds_v4(read_l + mbo + r * 64 + 32, l_od[r][0], l_od[r][1], l_od[r][2], l_od[r][3]);
+            lds_v4(read_l + mbo + r * 64 + 48, l_od[r][4], l_od[r][5], l_od[r][6], l_od[r][7]);
+          }
         }
-        if (lane == 31 || last_x) {
-          const bool from_mail = cross && !last_x;
-          const float* src = mb + ((q + 1) * 2 + 0) * 32;
+        if (last_x) {
 #pragma unroll
           for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              r_le[r][j] = from_mail ? src[r * 16 + j] : 0.f;
-              r_od[r][j] = from_mail ? src[r * 16 + 8 + j] : 0.f;
-            }
+            for (int j = 0; j < 8; ++j) r_le[r][j] = r_od[r][j] = 0.f;
+        } else if (cross && lane == 31) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            lds_v4(read_r + mbo + r * 64, r_le[r][0], r_le[r][1], r_le[r][2], r_le[r][3]);
+            lds_v4(read_r + mbo + r * 64 + 16, r_le[r][4], r_le[r][5], r_le[r][6], r_le[r][7]);
+            lds_v4(read_r + mbo + r * 64 + 32, r_od[r][0], r_od[r][1], r_od[r][2], r_od[r][3]);
+            lds_v4(read_r + mbo + r * 64 + 48, r_od[r][4], r_od[r][5], r_od[r][6], r_od[r][7]);
+          }
         }
+        if constexpr (PROF) tq[7] = clock64();
         float hf[2][2][8];                       // [t row E/O][output column 2x / 2x+1][channel]
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -416,13 +479,12 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
         }
         if constexpr (PROF) tq[4] = clock64();
-        if (emit) {
+        if (y >= it.y_emit) {                      // warp- and pair-uniform
           // output rows Y0 = 2y-2 (t rows 2y-3..2y) and Y1 = 2y-1 (t rows 2y-2..2y+1)
+          uint32_t keep[4][4];                     // [yi*2+xi]: this half's 8 channels of ITS plane
 #pragma unroll
           for (int yi = 0; yi < 2; ++yi) {
-            const int Y = 2 * y - 2 + yi;
             const float2 nz = yi == 0 ? nz0 : nz1;
-            const size_t prow = (img_row0 + Y) * (Wo + 1);
 #pragma unroll
             for (int xi = 0; xi < 2; ++xi) {
               uint32_t hw[4], lw[4];
@@ -451,16 +513,42 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 hw[j2] = hu;
                 lw[j2] = *reinterpret_cast<const uint32_t*>(&ll);
               }
-              const size_t off = (prow + 2 * x + xi) * p.Cout + c0;
-              *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              const int pc = yi * 2 + xi;
+              if (h == 0) {
+                sts_v4u(pair_send + pc * (32 * 16), lw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) keep[pc][i] = hw[i];
+              } else {
+                sts_v4u(pair_send + pc * (32 * 16), hw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) keep[pc][i] = lw[i];
+              }
             }
-            if (last_x) {                          // zero pad column of the output grid
-              const size_t off = (prow + Wo) * p.Cout + c0;
+          }
+          named_bar_sync(3 + q, 64);               // both halves of this lane quarter have posted
+          __nv_bfloat16* plane = (h == 0) ? out_hi : out_lo;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint32_t other[4];
+            lds_v4u(pair_recv + pc * (32 * 16), other);
+            const int Y = 2 * y - 2 + (pc >> 1);
+            const size_t off = ((img_row0 + Y) * (Wo + 1) + 2 * x + (pc & 1)) * p.Cout + it.cg * UNC;
+            if (img_ok && (!PROF || p.debug_nostore == 0 || keep[pc][0] == 0x12345678u)) {
+              if (h == 0) stg_256(plane + off, keep[pc], other);     // channels 0-7 | 8-15
+              else stg_256(plane + off, other, keep[pc]);
+            }
+          }
+          named_bar_sync(3 + q, 64);               // the exchange area may be overwritten
+          if (img_ok && last_x) {                  // zero pad column of the output grid
+#pragma unroll
+            for (int yi = 0; yi < 2; ++yi) {
+              const size_t off = ((img_row0 + 2 * y - 2 + yi) * (Wo + 1) + Wo) * p.Cout + c0;
               *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(0u, 0u, 0u, 0u);
               *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(0u, 0u, 0u, 0u);
             }
           }
+        }
+        if (emit) {
           if (y == p.H) {                          // last step of the image: zero pad row
             const size_t prow = (img_row0 + Ho) * (Wo + 1);
 #pragma unroll
@@ -475,9 +563,14 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         }
         if constexpr (PROF) {
           tq[5] = clock64();
-#pragma unroll
-          for (int i = 0; i < 5; ++i) prof_acc[i] += tq[i + 1] - tq[i];
-          prof_acc[5] += 1;
+          prof_acc[0] += tq[1] - tq[0];
+          prof_acc[1] += tq[2] - tq[1];
+          prof_acc[2] += tq[3] - tq[2];
+          prof_acc[3] += tq[6] - tq[3];
+          prof_acc[4] += tq[7] - tq[6];
+          prof_acc[5] += tq[4] - tq[7];
+          prof_acc[6] += tq[5] - tq[4];
+          prof_acc[7] += 1;
         }
         // slide the vertical window: rows 2y-1, 2y, 2y+1 become 2(y+1)-3 .. 2(y+1)-1
 #pragma unroll
@@ -492,9 +585,9 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     if constexpr (PROF) {
       if (lane == 0 && p.debug_prof != nullptr) {
-        long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 6;
+        long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 8;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) dst[i] = prof_acc[i];
+        for (int i = 0; i < 8; ++i) dst[i] = prof_acc[i];
       }
     }
   }

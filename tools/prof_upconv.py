@@ -29,7 +29,7 @@ def main():
     kern = (torch.tensor([1., 3., 3., 1.])[:, None] * torch.tensor([1., 3., 3., 1.])[None, :] / 16).to(dev)
     nh = torch.empty((B * (Ho + 1) * (Ho + 1), Cout), dtype=torch.bfloat16, device=dev)
     nl = torch.empty_like(nh)
-    prof = torch.zeros(148, 8, 6, dtype=torch.int64, device=dev)
+    prof = torch.zeros(148, 8, 8, dtype=torch.int64, device=dev)
     args = (ops._p(planes.hi), ops._p(planes.lo), ops._p(u_hi), ops._p(u_lo), ops._p(dm), ops._p(kern),
             ops._p(noise), noise.stride(0), ops._p(nw), ops._p(bias), ops._p(ns), ops._p(nh), ops._p(nl),
             B, Cin, Cout, H, H)
@@ -45,11 +45,11 @@ def main():
     _cabi.call('rw_debug_upconv_profile', *args, ops._p(prof), ops._stream())
     torch.cuda.synchronize()
     p = prof.cpu().double()
-    steps = p[:, :, 5].sum()
-    names = ['wait MMA', 'TMEM drain', 'combine+mailbox+barrier', 'exchange+horizontal FIR',
-             'vertical FIR+activation+stores']
-    tot = p[:, :, :5].sum()
-    print('steps per epilogue warp (avg) %.1f, cycles per step %.0f' % (steps / (p[:, :, 5] > 0).sum(), tot / steps))
+    steps = p[:, :, 7].sum()
+    names = ['wait MMA', 'TMEM drain', 'combine+mailbox+barrier', 'shuffles', 'edge-lane fix-ups',
+             'horizontal FIR', 'vertical FIR+activation+stores']
+    tot = p[:, :, :7].sum()
+    print('steps per epilogue warp (avg) %.1f, cycles per step %.0f' % (steps / (p[:, :, 7] > 0).sum(), tot / steps))
     for i, n in enumerate(names):
         print('  %-34s %7.0f cycles/step  %5.1f %%' % (n, p[:, :, i].sum() / steps, 100 * p[:, :, i].sum() / tot))
 
