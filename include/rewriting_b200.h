@@ -290,9 +290,9 @@ int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const
                      int rows, int Cm, int Cn, int lbo_bytes, int sbo_bytes, float* out,
                      void* workspace, size_t workspace_bytes, rw_stream_t stream);
 
-/* rw_modconv_up_fused instrumented with clock64(): prof_out[grid][8 epilogue warps][6] = cycles in
- * {wait for the MMAs, TMEM drain, combine + mailbox + barrier, neighbour exchange + horizontal FIR,
- * vertical FIR + activation + stores} and the step count */
+/* rw_modconv_up_fused instrumented with clock64(): prof_out[grid][8 epilogue warps][8] = cycles in
+ * {wait for the MMAs, TMEM drain, combine + mailbox + barrier, shuffles, edge-lane fix-ups,
+ * horizontal FIR, vertical FIR + activation + stores} and the step count */
 int rw_debug_upconv_profile(const void* kp_hi, const void* kp_lo, const void* wt_hi,
                             const void* wt_lo, const float* demod, const float* kernel4x4,
                             const float* noise, long long noise_bstride, const float* noise_w,
