@@ -113,6 +113,43 @@ int make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4]
   return RW_OK;
 }
 
+// general form: rank <= 5, element strides (a stride s on dimension d loads every s-th element
+// of the box extent box[d]), swizzle 0 = none, 1 = 32 B, 2 = 128 B
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estrides,
+                      int swizzle) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return RW_ERR_NO_DRIVER_SYMBOL;
+  }
+  if (rank < 2 || rank > 5 || (reinterpret_cast<uintptr_t>(base) & 0xF) != 0) {
+    set_last_error("TMA operand: rank %d, ptr %p (must be rank 2..5, 16-byte aligned)", rank, base);
+    return RW_ERR_BAD_ARG;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estrides ? estrides[i] : 1u;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  const CUtensorMapSwizzle sw = swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(rank %d) failed: CUresult %d (dim0 %llu dim1 %llu box %u %u)",
+                   rank, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0],
+                   box[1]);
+    return RW_ERR_CUDA;
+  }
+  return RW_OK;
+}
+
 // split heuristic shared by the workspace query and the launches
 static int gram_splits(int tiles, long long rows, int ntaps) {
   const long long total_rb = (rows + 63) / 64;

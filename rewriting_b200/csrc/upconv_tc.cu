@@ -57,8 +57,10 @@ constexpr int kUBBytes = UN * UBK * 2;  // one plane of B: 18 KB
 constexpr int kUStageBytes = 2 * kUABytes + 2 * kUBBytes;    // 68 KB
 constexpr int kUAccStride = 256;        // TMEM columns between the two accumulators
 constexpr int kUMailFloats = 2 * 2 * 4 * 2 * 32;             // [buf][half][quarter][side][32]
-constexpr int kUPairBytes = 4 * 2 * 4 * 32 * 16;               // [quarter][sender half][piece][lane][16 B]
-constexpr int kUSmemTotal = kUStages * kUStageBytes + kUMailFloats * 4 + kUPairBytes + 1024 + 256;
+constexpr int kUOutSlotBytes = 64 * 32;                      // 64 output pixels x 16 channels, one plane
+constexpr int kUOutQuarterBytes = 2 * kUOutSlotBytes;        // hi + lo slot of a lane quarter
+constexpr int kUOutStageBytes = 4 * kUOutQuarterBytes;       // 16 KB
+constexpr int kUSmemTotal = kUStages * kUStageBytes + kUMailFloats * 4 + kUOutStageBytes + 1024 + 256;
 
 struct UBarriers {
   uint64_t full[kUStages];
@@ -68,25 +70,14 @@ struct UBarriers {
   uint32_t tmem_base;
 };
 
-// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3,
+                                            int32_t c4) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
-                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
       : "memory");
 }
 
@@ -108,29 +99,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
-// vector accesses to the mailbox by 32-bit shared-window address: an edge lane moves its 32
-// values with 8 x 128-bit instructions.  (As 64 scalar loads through the generic `mail` pointer
-// inside a one-lane divergent block, this fix-up took 2 980 of a step's 7 800 cycles:
-// tools/prof_upconv.py.)
+// vector accesses to the mailbox by 32-bit shared-window address
 __device__ __forceinline__ void sts_v4(uint32_t a, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w)
-               : "memory");
-}
-__device__ __forceinline__ void sts_v4u(uint32_t a, const uint32_t (&w)[4]) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-               "r"(w[3])
-               : "memory");
-}
-__device__ __forceinline__ void lds_v4u(uint32_t a, uint32_t (&w)[4]) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
-               : "r"(a)
-               : "memory");
-}
-// one full 32-byte sector per thread (sm_100: 256-bit global store)
-__device__ __forceinline__ void stg_256(void* dst, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(a[0]),
-               "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
                : "memory");
 }
 __device__ __forceinline__ void lds_v4(uint32_t a, float& x, float& y, float& z, float& w) {
@@ -174,20 +145,59 @@ __device__ __forceinline__ UpItem decode_item(int item, const UpFusedParams& p) 
   return it;
 }
 
+// tcgen05.ld.16x256b.x1: 16 TMEM lanes x 8 fp32 columns; thread t receives lane t/4, columns
+// 2(t%4), 2(t%4)+1 in r[0], r[1] and lane t/4 + 8, same columns, in r[2], r[3]
+// (tools/probe/probe_sm100.cu prints the distribution on the device)
+__device__ __forceinline__ void tmem_ld_16x256(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// four 8x8 b16 matrices: register i of lane t is row t/4, 32-bit column t%4 of matrix i; lane t
+// supplies the address of row t%8 of matrix t/8
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(addr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
 // PROF = true: bring-up variant that accumulates, per epilogue warp, the cycles spent in each phase
-// of a step (tools/debug_upconv.py prof) into p.debug_prof; the product launches PROF = false.
+// of a step (tools/prof_upconv.py) into p.debug_prof; the product launches PROF = false.
 template <bool PROF>
 __global__ void __launch_bounds__(kUThreads, 1)
 upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi,
-                    const __grid_constant__ CUtensorMap map_w_lo, const UpFusedParams p) {
+                    const __grid_constant__ CUtensorMap map_w_lo,
+                    const __grid_constant__ CUtensorMap map_o_hi,
+                    const __grid_constant__ CUtensorMap map_o_lo, const UpFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   float* mail = reinterpret_cast<float*>(smem + kUStages * kUStageBytes);
-  uint8_t* pair_area = smem + kUStages * kUStageBytes + kUMailFloats * 4;
-  UBarriers* bars = reinterpret_cast<UBarriers*>(pair_area + kUPairBytes);
+  uint8_t* out_stage = smem + kUStages * kUStageBytes + kUMailFloats * 4;
+  UBarriers* bars = reinterpret_cast<UBarriers*>(out_stage + kUOutStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,6 +209,8 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_w_hi);
     tma_prefetch_desc(&map_w_lo);
+    tma_prefetch_desc(&map_o_hi);
+    tma_prefetch_desc(&map_o_lo);
     for (int s = 0; s < kUStages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -219,25 +231,44 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     reg_dealloc<40>();
   if (warp == kUTmaWarp) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-        const UpItem it = decode_item(item, p);
-        const int b0 = it.bg * G;
-        const int wrow = it.cg * UN;
-        for (int y = it.y_first; y < it.y_end; ++y) {
-          for (int kb = 0; kb < kb_count; ++kb) {
+    // The A tile's rows are PERMUTED: inside every 32-pixel quarter, tile row 8 j + g holds pixel
+    // 4 g + j (j < 4, g < 8), so that tcgen05.ld.16x256b hands an epilogue thread four ADJACENT
+    // pixels.  The permutation is free: the tensor map lists the key planes' dimensions as
+    // (channel, x / 4 % 8, x % 4, x / 32, row) — TMA fills shared memory in that order — so one
+    // load still brings a whole image row (W >= 32; W < 32: (channel, x / 4, image, x % 4, y), one
+    // load per quarter).  [Loading the eight rows of each (quarter, j) separately — 32 one-KB
+    // boxes per plane and stage, strided or not — fed the MMAs at a third of their rate.]
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool wide = p.W >= 32;
+    const int nop = wide ? G : 4;                  // loads per plane and stage
+    const int plane = lane / nop, idx = lane % nop;
+    const CUtensorMap* amap = plane ? &map_a_lo : &map_a_hi;
+    const CUtensorMap* wmap = (lane & 1) ? &map_w_lo : &map_w_hi;
+    const uint32_t a_off = plane * kUABytes + idx * (kUABytes / nop);
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const UpItem it = decode_item(item, p);
+      const int b0 = it.bg * G;
+      const int wrow = it.cg * UN;
+      for (int y = it.y_first; y < it.y_end; ++y) {
+        for (int kb = 0; kb < kb_count; ++kb) {
+          if (lane == 0) {
             mbar_wait_relaxed(&bars->empty[stage], phase ^ 1u);
-            uint8_t* st = smem + stage * kUStageBytes;
             mbar_expect_tx(&bars->full[stage], kUStageBytes);
-            tma_load_4d(st, &map_a_hi, &bars->full[stage], kb * UBK, 0, y, b0);
-            tma_load_4d(st + kUABytes, &map_a_lo, &bars->full[stage], kb * UBK, 0, y, b0);
-            tma_load_2d(st + 2 * kUABytes, &map_w_hi, &bars->full[stage], kb * UBK, wrow);
-            tma_load_2d(st + 2 * kUABytes + kUBBytes, &map_w_lo, &bars->full[stage], kb * UBK,
-                        wrow);
-            if (++stage == kUStages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          uint8_t* st = smem + stage * kUStageBytes;
+          if (lane < 2 * nop) {
+            if (wide)
+              tma_load_5d(st + a_off, amap, &bars->full[stage], kb * UBK, 0, 0, 0,
+                          (b0 + idx) * (p.H + 1) + y);
+            else
+              tma_load_5d(st + a_off, amap, &bars->full[stage], kb * UBK, 0, b0 + idx * (32 / p.W), 0, y);
+          } else if (lane >= 30) {
+            tma_load_2d(st + 2 * kUABytes + (lane & 1) * kUBBytes, wmap, &bars->full[stage], kb * UBK,
+                        wrow);
+          }
+          if (++stage == kUStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -282,16 +313,21 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   }
   } else {
     // ------------------------------ epilogue ----------------------------------
+    // thread (g = lane / 4, c = lane % 4) of warp (q, h) owns the four adjacent pixels
+    // 32 q + 4 g + j of the tile and the two output channels 8 h + 2 c + e of the item's sixteen:
+    // "unit" u = 2 j + e indexes its eight (pixel, channel) pairs.
     reg_alloc<232>();
     const int q = warp & 3;
     const int h = warp >> 2;
-    const int l = q * 32 + lane;               // tile lane = TMEM lane
+    const int g = lane >> 2, c = lane & 3;
     const int W = p.W;
-    const int x = l & (W - 1);
-    const int img_in_tile = l / W;
+    const int T0 = q * 32 + 4 * g;             // tile index of the first of the four pixels
+    const int x0 = T0 & (W - 1);
+    const int img_in_tile = T0 / W;
     const int Ho = 2 * p.H, Wo = 2 * W;
-    const bool first_x = (x == 0), last_x = (x == W - 1);
+    const bool first_x = (x0 == 0), last_x = (x0 + 4 == W);
     const bool cross = W > 32;                 // x-neighbours can live in another warp
+    const bool mail_l = cross && g == 0 && !first_x, mail_r = cross && g == 7 && !last_x;
     // flipped blur kernel (upfirdn2d correlates with the flipped kernel), rank one:
     //   kf[a][b] = kv[a] * kh[b],  kv[a] = kf[a][0],  kh[b] = kf[0][b] / kf[0][0]
     float kv[4], kh[4];
@@ -305,60 +341,73 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     const float nw = __ldg(p.noise_w);
     uint32_t step = 0;
-    // mailbox slots of this warp, as shared-window byte addresses (buffer 0; +kMailBufBytes for
-    // odd steps): slot (h, q, side) = 32 floats [row E/O][ro|le, od][8 channels]
+    // mailbox across quarter boundaries (W > 32): slot (h, q, side) = 4 lanes (c) x 8 floats
+    // [t row E/O][ro|le e0, e1, od e0, e1]; double buffered by step parity
     constexpr uint32_t kMailBufBytes = 2 * 4 * 2 * 32 * 4;
-    const uint32_t mail_s = smem_u32(mail) + h * (4 * 2 * 32 * 4);
+    const uint32_t mail_s = smem_u32(mail) + h * (4 * 2 * 32 * 4) + c * 32;
     const uint32_t post_r = mail_s + (q * 2 + 1) * 128, post_l = mail_s + (q * 2 + 0) * 128;
     const uint32_t read_l = mail_s + ((q - 1) * 2 + 1) * 128, read_r = mail_s + ((q + 1) * 2 + 0) * 128;
-    // partner exchange (the two warps of a lane quarter own 8 channels each = half of every
-    // 32-byte sector of the output planes): half 0 stores the `hi` plane, half 1 the `lo` plane;
-    // each sends the 16-byte pieces of the OTHER plane to its partner through shared memory and
-    // writes whole sectors with 256-bit stores.  [piece][lane][16 B] keeps the STS/LDS conflict-free.
-    const uint32_t pair_s = smem_u32(pair_area) + q * (2 * 4 * 32 * 16);
-    const uint32_t pair_send = pair_s + h * (4 * 32 * 16) + lane * 16;
-    const uint32_t pair_recv = pair_s + (h ^ 1) * (4 * 32 * 16) + lane * 16;
+    // output staging of this quarter: slot 0 = `hi` plane, slot 1 = `lo` plane of ONE output row
+    // segment (64 pixels x 16 channels), in the order the 5-d store map reads it,
+    // [image][pixel % 8][pixel / 8][16 channels], 32-byte swizzle.  stmatrix row addresses: lane
+    // supplies row g' = lane % 8 of matrix m = lane / 8 (= pixel 4 g' + m of the quarter).
+    const uint32_t slot_s = smem_u32(out_stage) + q * kUOutQuarterBytes;
+    uint32_t st_addr[2];
+    {
+      const int m = lane >> 3, gp = lane & 7;
+      const int Wm = W < 32 ? W : 32;
+      const int tl = 4 * gp + m;
+      const int il = tl / W;                          // image inside the quarter (W < 32)
+      const int xg = ((4 * gp) & (Wm - 1)) >> 2;
+#pragma unroll
+      for (int xi = 0; xi < 2; ++xi) {
+        uint32_t a = slot_s + (((il * 8 + 2 * m + xi) * (Wm >> 2) + xg) << 5) + (h << 4);
+        a ^= ((a >> 7) & 1u) << 4;
+        st_addr[xi] = a;
+      }
+    }
+    const CUtensorMap* omap = h ? &map_o_lo : &map_o_hi;   // warp (q, h) issues plane h's stores
+    const uint32_t my_slot = slot_s + h * kUOutSlotBytes;
+    const int o_xg = ((32 * q) & (W - 1)) >> 2;
+    const int o_img = (32 * q) / W;
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, shuffles, fixups, hf, emit, steps
 
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const UpItem it = decode_item(item, p);
-      const int b = it.bg * G + img_in_tile;
+      const int b0 = it.bg * G;
+      const int b = b0 + img_in_tile;
       const bool img_ok = b < p.B;
-      const int c0 = it.cg * UNC + h * 8;      // first of this thread's 8 output channels
-      float dm[8], bs[8], ns[8];
+      const int c0 = it.cg * UNC + h * 8 + 2 * c;     // first of this thread's 2 output channels
+      float dm[2], bs[2], ns[2];
       {
         const size_t o = static_cast<size_t>(img_ok ? b : 0) * p.Cout + c0;
-#pragma unroll
-        for (int j4 = 0; j4 < 2; ++j4) {
-          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.demod + o) + j4);
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j4);
-          const float4 n4 = __ldg(reinterpret_cast<const float4*>(p.next_scale + o) + j4);
-          dm[4 * j4] = d4.x; dm[4 * j4 + 1] = d4.y; dm[4 * j4 + 2] = d4.z; dm[4 * j4 + 3] = d4.w;
-          bs[4 * j4] = b4.x; bs[4 * j4 + 1] = b4.y; bs[4 * j4 + 2] = b4.z; bs[4 * j4 + 3] = b4.w;
-          ns[4 * j4] = n4.x; ns[4 * j4 + 1] = n4.y; ns[4 * j4 + 2] = n4.z; ns[4 * j4 + 3] = n4.w;
-        }
+        const float2 d2 = __ldg(reinterpret_cast<const float2*>(p.demod + o));
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+        const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.next_scale + o));
+        dm[0] = d2.x; dm[1] = d2.y;
+        bs[0] = b2.x; bs[1] = b2.y;
+        ns[0] = n2.x; ns[1] = n2.y;
       }
       // vertical state: u = 2 taps of the previous input row, and the horizontally filtered
-      // t rows 2y-3 (w0), 2y-2 (w1), 2y-1 (w2); each [2 output columns][8 channels]
+      // t rows 2y-3 (w0), 2y-2 (w1), 2y-1 (w2); each [2 output columns][8 units]
       float c20[8], c21[8], c22[8];
       float w0[2][8], w1[2][8], w2[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        c20[j] = c21[j] = c22[j] = 0.f;
-        w0[0][j] = w0[1][j] = w1[0][j] = w1[1][j] = w2[0][j] = w2[1][j] = 0.f;
+      for (int u = 0; u < 8; ++u) {
+        c20[u] = c21[u] = c22[u] = 0.f;
+        w0[0][u] = w0[1][u] = w1[0][u] = w1[1][u] = w2[0][u] = w2[1][u] = 0.f;
       }
-      const float* nrow_base = p.noise + static_cast<size_t>(img_ok ? b : 0) * p.noise_bstride + 2 * x;
+      const float* nrow_base = p.noise + static_cast<size_t>(img_ok ? b : 0) * p.noise_bstride + 2 * x0;
       __nv_bfloat16* out_hi = static_cast<__nv_bfloat16*>(p.next_hi);
       __nv_bfloat16* out_lo = static_cast<__nv_bfloat16*>(p.next_lo);
       const size_t img_row0 = static_cast<size_t>(img_ok ? b : 0) * (Ho + 1);
 
       for (int y = it.y_first; y < it.y_end; ++y, ++step) {
-        const bool emit = (y >= it.y_emit) && img_ok;
-        // noise of the two output rows of this step (issued before the TMEM wait)
-        float2 nz0 = make_float2(0.f, 0.f), nz1 = make_float2(0.f, 0.f);
-        if (emit) {
-          nz0 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 2) * Wo));
-          nz1 = __ldg(reinterpret_cast<const float2*>(nrow_base + static_cast<size_t>(2 * y - 1) * Wo));
+        const bool rows_out = (y >= it.y_emit);   // warp-, pair- and CTA-uniform
+        const bool emit = rows_out && img_ok;
+        if (emit && c < 2) {                       // noise of the two output rows -> L1
+          const float* np = nrow_base + static_cast<size_t>(2 * y - 2 + c) * Wo;
+          asm volatile("prefetch.global.L1 [%0];\n" ::"l"(np));
         }
         long long tq[8];
         if constexpr (PROF) tq[0] = clock64();
@@ -371,193 +420,171 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                               (static_cast<uint32_t>(q * 32) << 16);
         float P[9][8];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) tmem_ld_32x8(tcol + t * UNC, P[t]);
+        for (int t = 0; t < 9; ++t) {
+          tmem_ld_16x256(tcol + t * UNC, &P[t][0]);                  // pixels j = 0, 1
+          tmem_ld_16x256(tcol + t * UNC + (16u << 16), &P[t][4]);    // pixels j = 2, 3
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
         if constexpr (PROF) tq[2] = clock64();
         if (p.debug_p != nullptr && img_ok && y < p.H && y >= it.y_emit - 1) {
-          float* dp = p.debug_p + ((static_cast<size_t>(b) * p.H + y) * W + x) * 9 * p.Cout + c0;
 #pragma unroll
-          for (int t = 0; t < 9; ++t)
+          for (int u = 0; u < 8; ++u) {
+            float* dp = p.debug_p + ((static_cast<size_t>(b) * p.H + y) * W + x0 + (u >> 1)) * 9 * p.Cout +
+                        c0 + (u & 1);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dp[t * p.Cout + j] = P[t][j];
+            for (int t = 0; t < 9; ++t) dp[t * p.Cout] = P[t][u];
+          }
         }
 
-        // t rows E = 2y, O = 2y+1 in lane-local pieces (see the header comment):
+        // t rows E = 2y, O = 2y+1 in pixel-local pieces (see the header comment):
         //   E.e[x] = leE[x] + rE[x-1], E.o[x] = oE[x];   O.e[x] = leO[x] + rO[x-1], O.o[x] = oO[x]
         float le[2][8], ro[2][8], od[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          le[0][j] = P[0][j] + c20[j];
-          od[0][j] = P[1][j] + c21[j];
-          ro[0][j] = P[2][j] + c22[j];
-          le[1][j] = P[3][j];
-          od[1][j] = P[4][j];
-          ro[1][j] = P[5][j];
-          c20[j] = P[6][j];
-          c21[j] = P[7][j];
-          c22[j] = P[8][j];
+        for (int u = 0; u < 8; ++u) {
+          le[0][u] = P[0][u] + c20[u];
+          od[0][u] = P[1][u] + c21[u];
+          ro[0][u] = P[2][u] + c22[u];
+          le[1][u] = P[3][u];
+          od[1][u] = P[4][u];
+          ro[1][u] = P[5][u];
+          c20[u] = P[6][u];
+          c21[u] = P[7][u];
+          c22[u] = P[8][u];
         }
-        // mailbox across warp boundaries: lane 31 posts (ro, od) for its right neighbour,
-        // lane 0 posts (le, od) for its left neighbour
+        // mailbox across quarter boundaries: the g = 7 lanes post (ro, od) of their last pixel for
+        // the right-hand quarter, the g = 0 lanes post (le, od) of their first pixel
         const uint32_t mbo = (step & 1u) * kMailBufBytes;
         if (cross) {
-          if (lane == 31) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              sts_v4(post_r + mbo + r * 64, ro[r][0], ro[r][1], ro[r][2], ro[r][3]);
-              sts_v4(post_r + mbo + r * 64 + 16, ro[r][4], ro[r][5], ro[r][6], ro[r][7]);
-              sts_v4(post_r + mbo + r * 64 + 32, od[r][0], od[r][1], od[r][2], od[r][3]);
-              sts_v4(post_r + mbo + r * 64 + 48, od[r][4], od[r][5], od[r][6], od[r][7]);
-            }
+          if (g == 7) {
+            sts_v4(post_r + mbo, ro[0][6], ro[0][7], od[0][6], od[0][7]);
+            sts_v4(post_r + mbo + 16, ro[1][6], ro[1][7], od[1][6], od[1][7]);
           }
-          if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              sts_v4(post_l + mbo + r * 64, le[r][0], le[r][1], le[r][2], le[r][3]);
-              sts_v4(post_l + mbo + r * 64 + 16, le[r][4], le[r][5], le[r][6], le[r][7]);
-              sts_v4(post_l + mbo + r * 64 + 32, od[r][0], od[r][1], od[r][2], od[r][3]);
-              sts_v4(post_l + mbo + r * 64 + 48, od[r][4], od[r][5], od[r][6], od[r][7]);
-            }
+          if (g == 0) {
+            sts_v4(post_l + mbo, le[0][0], le[0][1], od[0][0], od[0][1]);
+            sts_v4(post_l + mbo + 16, le[1][0], le[1][1], od[1][0], od[1][1]);
           }
           named_bar_sync(1 + h, 128);
         }
         if constexpr (PROF) tq[3] = clock64();
-        // neighbour pieces: left (ro, od) of lane x-1, right (le, od) of lane x+1
-        float l_ro[2][8], l_od[2][8], r_le[2][8], r_od[2][8];
+        // the only pieces that come from other threads: left (ro, od) of pixel 4g-1 (lane - 4),
+        // right (le, od) of pixel 4g+4 (lane + 4); [t row][e]
+        float Lro[2][2], Lod[2][2], Rle[2][2], Rod[2][2];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            l_ro[r][j] = __shfl_up_sync(0xffffffffu, ro[r][j], 1);
-            l_od[r][j] = __shfl_up_sync(0xffffffffu, od[r][j], 1);
-            r_le[r][j] = __shfl_down_sync(0xffffffffu, le[r][j], 1);
-            r_od[r][j] = __shfl_down_sync(0xffffffffu, od[r][j], 1);
+          for (int e = 0; e < 2; ++e) {
+            Lro[r][e] = __shfl_up_sync(0xffffffffu, ro[r][6 + e], 4);
+            Lod[r][e] = __shfl_up_sync(0xffffffffu, od[r][6 + e], 4);
+            Rle[r][e] = __shfl_down_sync(0xffffffffu, le[r][e], 4);
+            Rod[r][e] = __shfl_down_sync(0xffffffffu, od[r][e], 4);
           }
         if constexpr (PROF) tq[6] = clock64();
         if (first_x) {                            // image edge: nothing to the left
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) l_ro[r][j] = l_od[r][j] = 0.f;
-        } else if (cross && lane == 0) {          // left neighbour lives in the previous warp
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            lds_v4(read_l + mbo + r * 64, l_ro[r][0], l_ro[r][1], l_ro[r][2], l_ro[r][3]);
-            lds_v4(read_l + mbo + r * 64 + 16, l_ro[r][4], l_ro[r][5], l_ro[r][6], l_ro[r][7]);
-            lds_v4(read_l + mbo + r * 64 + 32, l_od[r][0], l_od[r][1], l_od[r][2], l_od[r][3]);
-            lds_v4(read_l + mbo + r * 64 + 48, l_od[r][4], l_od[r][5], l_od[r][6], l_od[r][7]);
-          }
+          for (int r = 0; r < 2; ++r) Lro[r][0] = Lro[r][1] = Lod[r][0] = Lod[r][1] = 0.f;
+        } else if (mail_l) {                      // left neighbour lives in the previous quarter
+          lds_v4(read_l + mbo, Lro[0][0], Lro[0][1], Lod[0][0], Lod[0][1]);
+          lds_v4(read_l + mbo + 16, Lro[1][0], Lro[1][1], Lod[1][0], Lod[1][1]);
         }
         if (last_x) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r_le[r][j] = r_od[r][j] = 0.f;
-        } else if (cross && lane == 31) {
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            lds_v4(read_r + mbo + r * 64, r_le[r][0], r_le[r][1], r_le[r][2], r_le[r][3]);
-            lds_v4(read_r + mbo + r * 64 + 16, r_le[r][4], r_le[r][5], r_le[r][6], r_le[r][7]);
-            lds_v4(read_r + mbo + r * 64 + 32, r_od[r][0], r_od[r][1], r_od[r][2], r_od[r][3]);
-            lds_v4(read_r + mbo + r * 64 + 48, r_od[r][4], r_od[r][5], r_od[r][6], r_od[r][7]);
-          }
+          for (int r = 0; r < 2; ++r) Rle[r][0] = Rle[r][1] = Rod[r][0] = Rod[r][1] = 0.f;
+        } else if (mail_r) {
+          lds_v4(read_r + mbo, Rle[0][0], Rle[0][1], Rod[0][0], Rod[0][1]);
+          lds_v4(read_r + mbo + 16, Rle[1][0], Rle[1][1], Rod[1][0], Rod[1][1]);
         }
         if constexpr (PROF) tq[7] = clock64();
-        float hf[2][2][8];                       // [t row E/O][output column 2x / 2x+1][channel]
+        float hf[2][2][8];                       // [t row E/O][output column 2x / 2x+1][unit]
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e0 = le[r][j] + l_ro[r][j];       // t col 2x
-            const float e1 = r_le[r][j] + ro[r][j];       // t col 2x+2
-            const float o0 = od[r][j];                    // t col 2x+1
-            hf[r][0][j] = fmaf(kh[3], e1, fmaf(kh[2], o0, fmaf(kh[1], e0, kh[0] * l_od[r][j])));
-            hf[r][1][j] = fmaf(kh[3], r_od[r][j], fmaf(kh[2], e1, fmaf(kh[1], o0, kh[0] * e0)));
+          for (int u = 0; u < 8; ++u) {
+            const float l_ro = u < 2 ? Lro[r][u & 1] : ro[r][u < 2 ? u : u - 2];
+            const float l_od = u < 2 ? Lod[r][u & 1] : od[r][u < 2 ? u : u - 2];
+            const float r_le = u >= 6 ? Rle[r][u & 1] : le[r][u >= 6 ? u : u + 2];
+            const float r_od = u >= 6 ? Rod[r][u & 1] : od[r][u >= 6 ? u : u + 2];
+            const float e0 = le[r][u] + l_ro;           // t col 2x
+            const float e1 = r_le + ro[r][u];           // t col 2x+2
+            const float o0 = od[r][u];                  // t col 2x+1
+            hf[r][0][u] = fmaf(kh[3], e1, fmaf(kh[2], o0, fmaf(kh[1], e0, kh[0] * l_od)));
+            hf[r][1][u] = fmaf(kh[3], r_od, fmaf(kh[2], e1, fmaf(kh[1], o0, kh[0] * e0)));
           }
         }
         if constexpr (PROF) tq[4] = clock64();
-        if (y >= it.y_emit) {                      // warp- and pair-uniform
-          // output rows Y0 = 2y-2 (t rows 2y-3..2y) and Y1 = 2y-1 (t rows 2y-2..2y+1)
-          uint32_t keep[4][4];                     // [yi*2+xi]: this half's 8 channels of ITS plane
+        if (rows_out) {
+          // output rows Y0 = 2y-2 (t rows 2y-3..2y) and Y1 = 2y-1 (t rows 2y-2..2y+1): each is
+          // packed to bf16 hi/lo words, staged with stmatrix and stored by TMA (the 32-byte pieces
+          // of 64 pixels scatter over 64 lines: as LSU stores they cost a third of the step)
 #pragma unroll
           for (int yi = 0; yi < 2; ++yi) {
-            const float2 nz = yi == 0 ? nz0 : nz1;
+            const int Y = 2 * y - 2 + yi;
+            float nz[8];
+            {
+              const float4* np = reinterpret_cast<const float4*>(nrow_base + static_cast<size_t>(Y) * Wo);
+              const float4 a4 = __ldg(np), b4 = __ldg(np + 1);
+              nz[0] = a4.x; nz[1] = a4.y; nz[2] = a4.z; nz[3] = a4.w;
+              nz[4] = b4.x; nz[5] = b4.y; nz[6] = b4.z; nz[7] = b4.w;
+            }
+            uint32_t hw[2][4], lw[2][4];
 #pragma unroll
             for (int xi = 0; xi < 2; ++xi) {
-              uint32_t hw[4], lw[4];
-              const float nzv = nw * (xi == 0 ? nz.x : nz.y);
 #pragma unroll
-              for (int j2 = 0; j2 < 4; ++j2) {
+              for (int j = 0; j < 4; ++j) {
+                const float nzv = nw * nz[2 * j + xi];
                 float kk[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  const int j = 2 * j2 + e;
+                  const int u = 2 * j + e;
                   float v;
                   if (yi == 0)
-                    v = fmaf(kv[3], hf[0][xi][j],
-                             fmaf(kv[2], w2[xi][j], fmaf(kv[1], w1[xi][j], kv[0] * w0[xi][j])));
+                    v = fmaf(kv[3], hf[0][xi][u],
+                             fmaf(kv[2], w2[xi][u], fmaf(kv[1], w1[xi][u], kv[0] * w0[xi][u])));
                   else
-                    v = fmaf(kv[3], hf[1][xi][j],
-                             fmaf(kv[2], hf[0][xi][j], fmaf(kv[1], w2[xi][j], kv[0] * w1[xi][j])));
-                  v = (v * dm[j] + nzv) + bs[j];
+                    v = fmaf(kv[3], hf[1][xi][u],
+                             fmaf(kv[2], hf[0][xi][u], fmaf(kv[1], w2[xi][u], kv[0] * w1[xi][u])));
+                  v = (v * dm[e] + nzv) + bs[e];
                   v = fmaxf(v, 0.2f * v) * 1.4142135623730951f;
-                  kk[e] = ns[j] * v;
+                  kk[e] = ns[e] * v;
                 }
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(kk[0], kk[1]);
                 const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
                 const __nv_bfloat162 ll = __floats2bfloat162_rn(
                     kk[0] - __uint_as_float(hu << 16), kk[1] - __uint_as_float(hu & 0xffff0000u));
-                hw[j2] = hu;
-                lw[j2] = *reinterpret_cast<const uint32_t*>(&ll);
-              }
-              const int pc = yi * 2 + xi;
-              if (h == 0) {
-                sts_v4u(pair_send + pc * (32 * 16), lw);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) keep[pc][i] = hw[i];
-              } else {
-                sts_v4u(pair_send + pc * (32 * 16), hw);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) keep[pc][i] = lw[i];
+                hw[xi][j] = hu;
+                lw[xi][j] = *reinterpret_cast<const uint32_t*>(&ll);
               }
             }
-          }
-          named_bar_sync(3 + q, 64);               // both halves of this lane quarter have posted
-          __nv_bfloat16* plane = (h == 0) ? out_hi : out_lo;
+            // the slots are free once the previous row's stores have read them
+            if (lane == 0) tma_store_wait_read();
+            named_bar_sync(3 + q, 64);
 #pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            uint32_t other[4];
-            lds_v4u(pair_recv + pc * (32 * 16), other);
-            const int Y = 2 * y - 2 + (pc >> 1);
-            const size_t off = ((img_row0 + Y) * (Wo + 1) + 2 * x + (pc & 1)) * p.Cout + it.cg * UNC;
-            if (img_ok && (!PROF || p.debug_nostore == 0 || keep[pc][0] == 0x12345678u)) {
-              if (h == 0) stg_256(plane + off, keep[pc], other);     // channels 0-7 | 8-15
-              else stg_256(plane + off, other, keep[pc]);
+            for (int xi = 0; xi < 2; ++xi) {
+              stmatrix_x4(st_addr[xi], hw[xi]);
+              stmatrix_x4(st_addr[xi] + kUOutSlotBytes, lw[xi]);
             }
-          }
-          named_bar_sync(3 + q, 64);               // the exchange area may be overwritten
-          if (img_ok && last_x) {                  // zero pad column of the output grid
-#pragma unroll
-            for (int yi = 0; yi < 2; ++yi) {
-              const size_t off = ((img_row0 + 2 * y - 2 + yi) * (Wo + 1) + Wo) * p.Cout + c0;
+            fence_proxy_async_smem();
+            named_bar_sync(3 + q, 64);
+            if (lane == 0 && (!PROF || p.debug_nostore == 0))
+              tma_store_5d(omap, my_slot, it.cg * UNC, o_xg, 0, Y, b0 + o_img);
+            if (img_ok && last_x && c == 0) {       // zero pad column of the output grid
+              const size_t off = ((img_row0 + Y) * (Wo + 1) + Wo) * p.Cout + it.cg * UNC + h * 8;
               *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(0u, 0u, 0u, 0u);
               *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(0u, 0u, 0u, 0u);
             }
           }
         }
-        if (emit) {
-          if (y == p.H) {                          // last step of the image: zero pad row
-            const size_t prow = (img_row0 + Ho) * (Wo + 1);
+        if (emit && y == p.H) {                    // last step of the image: zero pad row
+          const size_t prow = (img_row0 + Ho) * (Wo + 1);
 #pragma unroll
-            for (int xi = 0; xi < 3; ++xi) {
-              if (xi < 2 || last_x) {
-                const size_t off = (prow + 2 * x + xi) * p.Cout + c0;
-                *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(0u, 0u, 0u, 0u);
-              }
+          for (int i = 0; i < 3; ++i) {
+            // lane c covers output pixels 2 x0 + 2c, +1; the last lane also the pad corner
+            if (i < 2 || (last_x && c == 3)) {
+              const size_t off = (prow + 2 * x0 + 2 * c + i) * p.Cout + it.cg * UNC + h * 8;
+              *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(0u, 0u, 0u, 0u);
             }
           }
         }
@@ -576,13 +603,14 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int xi = 0; xi < 2; ++xi)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            w0[xi][j] = w2[xi][j];
-            w1[xi][j] = hf[0][xi][j];
-            w2[xi][j] = hf[1][xi][j];
+          for (int u = 0; u < 8; ++u) {
+            w0[xi][u] = w2[xi][u];
+            w1[xi][u] = hf[0][xi][u];
+            w2[xi][u] = hf[1][xi][u];
           }
       }
     }
+    if (lane == 0) tma_store_wait_all();
     if constexpr (PROF) {
       if (lane == 0 && p.debug_prof != nullptr) {
         long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 8;
@@ -602,8 +630,9 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 
 }  // namespace
 
-int make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4],
-                      const uint64_t strides_bytes[3], const uint32_t box[4]);
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estrides,
+                      int swizzle);
 
 int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* a_lo,
                         const void* w_hi, const void* w_lo, cudaStream_t stream) {
@@ -635,16 +664,42 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
   p.nbands = best;
   p.nitems = nbg * p.ncg * p.nbands;
 
-  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-  const uint64_t dims[4] = {static_cast<uint64_t>(p.Cin), static_cast<uint64_t>(W + 1),
-                            static_cast<uint64_t>(H + 1), static_cast<uint64_t>(p.B)};
-  const uint64_t str[3] = {static_cast<uint64_t>(p.Cin) * 2,
-                           static_cast<uint64_t>(W + 1) * p.Cin * 2,
-                           static_cast<uint64_t>(H + 1) * (W + 1) * p.Cin * 2};
-  const uint32_t box[4] = {UBK, static_cast<uint32_t>(W), 1u, static_cast<uint32_t>(G)};
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo;
+  // key planes [B][H+1][W+1][Cin] with the dimensions listed so that shared memory receives the
+  // rows of a 32-pixel quarter in the order 8 (x % 4) + x / 4 (see the producer)
+  const uint32_t Wm = W < 32 ? W : 32;
+  const uint64_t kpx = static_cast<uint64_t>(p.Cin) * 2;
+  const uint64_t krow = static_cast<uint64_t>(W + 1) * kpx;
   int rc;
-  if ((rc = make_tmap_4d_bf16(&ma_hi, a_hi, dims, str, box))) return rc;
-  if ((rc = make_tmap_4d_bf16(&ma_lo, a_lo, dims, str, box))) return rc;
+  if (W >= 32) {
+    // (channel, x / 4 % 8, x % 4, x / 32, image * (H + 1) + y)
+    const uint64_t dims[5] = {static_cast<uint64_t>(p.Cin), 8, 4, static_cast<uint64_t>(W / 32),
+                              static_cast<uint64_t>(p.B) * (H + 1)};
+    const uint64_t str[4] = {4 * kpx, kpx, 32 * kpx, krow};
+    const uint32_t box[5] = {UBK, 8u, 4u, static_cast<uint32_t>(W / 32), 1u};
+    if ((rc = make_tmap_nd_bf16(&ma_hi, a_hi, 5, dims, str, box, nullptr, 2))) return rc;
+    if ((rc = make_tmap_nd_bf16(&ma_lo, a_lo, 5, dims, str, box, nullptr, 2))) return rc;
+  } else {
+    // (channel, x / 4, image, x % 4, y)
+    const uint64_t dims[5] = {static_cast<uint64_t>(p.Cin), static_cast<uint64_t>(W / 4),
+                              static_cast<uint64_t>(p.B), 4, static_cast<uint64_t>(H + 1)};
+    const uint64_t str[4] = {4 * kpx, static_cast<uint64_t>(H + 1) * krow, kpx, krow};
+    const uint32_t box[5] = {UBK, static_cast<uint32_t>(W / 4), 32u / Wm, 4u, 1u};
+    if ((rc = make_tmap_nd_bf16(&ma_hi, a_hi, 5, dims, str, box, nullptr, 2))) return rc;
+    if ((rc = make_tmap_nd_bf16(&ma_lo, a_lo, 5, dims, str, box, nullptr, 2))) return rc;
+  }
+  // output planes [B][Ho+1][Wo+1][Cout] seen as (channel, X / 8, X % 8, Y, image): one store = 16
+  // channels of a quarter's 64 output pixels, staged as [image][X % 8][X / 8][16 ch] so that the
+  // eight row addresses of a stmatrix fall into different banks (32-byte swizzle)
+  {
+    const uint64_t Wo = 2 * static_cast<uint64_t>(W), Ho = 2 * static_cast<uint64_t>(H);
+    const uint64_t px = static_cast<uint64_t>(p.Cout) * 2;
+    const uint64_t od[5] = {static_cast<uint64_t>(p.Cout), Wo / 8, 8, Ho + 1, static_cast<uint64_t>(p.B)};
+    const uint64_t os[4] = {8 * px, px, (Wo + 1) * px, (Ho + 1) * (Wo + 1) * px};
+    const uint32_t ob[5] = {UNC, Wm / 4, 8u, 1u, 32u / Wm};
+    if ((rc = make_tmap_nd_bf16(&mo_hi, p.next_hi, 5, od, os, ob, nullptr, 1))) return rc;
+    if ((rc = make_tmap_nd_bf16(&mo_lo, p.next_lo, 5, od, os, ob, nullptr, 1))) return rc;
+  }
   const uint64_t wrows = static_cast<uint64_t>(p.ncg) * UN;
   if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, p.Cin, wrows, static_cast<uint64_t>(p.Cin) * 2, UBK, UN)))
     return rc;
@@ -660,7 +715,7 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
       if (rc) return rc;
       attr_p = true;
     }
-    upconv_fused_kernel<true><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    upconv_fused_kernel<true><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, p);
     return check_cuda(cudaGetLastError(), "upconv_fused launch");
   }
   static bool attr_set = false;
@@ -671,7 +726,7 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
     if (rc) return rc;
     attr_set = true;
   }
-  upconv_fused_kernel<false><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  upconv_fused_kernel<false><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, p);
   return check_cuda(cudaGetLastError(), "upconv_fused launch");
 }
 
