@@ -290,9 +290,11 @@ int rw_debug_colgemm(const void* a_hi, const void* a_lo, const void* b_hi, const
                      int rows, int Cm, int Cn, int lbo_bytes, int sbo_bytes, float* out,
                      void* workspace, size_t workspace_bytes, rw_stream_t stream);
 
-/* rw_modconv_up_fused instrumented with clock64(): prof_out[grid][8 epilogue warps][8] = cycles in
+/* rw_modconv_up_fused instrumented with clock64(): prof_out[grid][8 epilogue warps][16] = cycles in
  * {wait for the MMAs, TMEM drain, combine + mailbox + barrier, shuffles, edge-lane fix-ups,
- * horizontal FIR, vertical FIR + activation + stores} and the step count */
+ * horizontal FIR, vertical FIR + activation + stores}, the step count, and the last phase split into
+ * {FIR + activation + bf16 split, wait for the staging slots, stmatrix + fence + pair barrier, TMA store issue} and
+ * the third of those into {stmatrix, fence.proxy.async, pair barrier} */
 int rw_debug_upconv_profile(const void* kp_hi, const void* kp_lo, const void* wt_hi,
                             const void* wt_lo, const float* demod, const float* kernel4x4,
                             const float* noise, long long noise_bstride, const float* noise_w,

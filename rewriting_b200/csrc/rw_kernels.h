@@ -73,7 +73,7 @@ struct UpFusedParams {
   int ncg, nbands, nitems;     // filled by the launcher
   float* debug_p;              // bring-up: raw tap products P[b][y][x][tap][Cout] (y < H), or null
   int debug_nostore;           // bring-up (profiling variant only): skip the plane stores
-  long long* debug_prof;       // bring-up: per (CTA, epilogue warp) cycle counters [grid][8][6], or null
+  long long* debug_prof;       // bring-up: per (CTA, epilogue warp) cycle counters [grid][8][16], or null
 };
 // weights: bf16 hi/lo planes [Cout/16][9 taps][16][Cin]  (rw_prep_weights, transpose_io = 2)
 int upconv_fused_launch(const UpFusedParams& p, const void* a_hi, const void* a_lo,

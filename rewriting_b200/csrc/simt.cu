@@ -149,7 +149,7 @@ __global__ void split_rows_kernel(const float* __restrict__ a, long long n,
 // prep_weights: W[Cout][Cin][3][3] fp32 -> (scale*W) as bf16 hi/lo planes
 //   transpose_io = 0: Wt[o][tap][i]            (forward conv / conv_transpose)
 //   transpose_io = 1: Wt[i][tap'][o]           (dgrad), tap' = 8 - tap if flip
-//   transpose_io = 2: Wt[o/16][tap][o%16][i]   (fused upsampling conv, upconv_tc.cu)
+//   transpose_io = 2: Wt[o/16][o%16/8][tap][o%8][i]   (fused upsampling conv, upconv_tc.cu)
 // and wsq[o][i] = sum_taps (scale*W)^2   (for demod, models.py:325-327)
 // one thread per (o, i)
 // ---------------------------------------------------------------------------
@@ -171,8 +171,9 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, int Cout, int C
     size_t dst;
     if (!transpose_io) {
       dst = (static_cast<size_t>(o) * 9 + tap) * Cin + i;
-    } else if (transpose_io == 2) {     // [Cout/16][tap][16][Cin]: the fused up-conv's N = 144 tiles
-      dst = ((static_cast<size_t>(o >> 4) * 9 + tap) * 16 + (o & 15)) * Cin + i;
+    } else if (transpose_io == 2) {     // [Cout/16][half][tap][8][Cin]: the fused up-conv's N = 144
+      // tiles; an epilogue warp reads the 72 columns of its channel half with two wide TMEM loads
+      dst = (((static_cast<size_t>(o >> 4) * 2 + ((o >> 3) & 1)) * 9 + tap) * 8 + (o & 7)) * Cin + i;
     } else {
       const int tp = flip_taps ? 8 - tap : tap;
       dst = (static_cast<size_t>(i) * 9 + tp) * Cout + o;

@@ -124,6 +124,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
+// named barriers: 1, 2 = mailbox of a channel half; 3 + q = the two warps of lane quarter q
+constexpr int kBarPair = 3;
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
 
 struct UpItem {
   int bg, band, cg;
@@ -147,7 +153,8 @@ __device__ __forceinline__ UpItem decode_item(int item, const UpFusedParams& p) 
 
 // tcgen05.ld.16x256b.x1: 16 TMEM lanes x 8 fp32 columns; thread t receives lane t/4, columns
 // 2(t%4), 2(t%4)+1 in r[0], r[1] and lane t/4 + 8, same columns, in r[2], r[3]
-// (tools/probe/probe_sm100.cu prints the distribution on the device)
+// (tools/probe/probe_sm100.cu prints the distribution on the device); .x8 repeats that for eight
+// consecutive groups of 8 columns, 4 registers each
 __device__ __forceinline__ void tmem_ld_16x256(uint32_t taddr, float* v) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];\n"
@@ -156,6 +163,19 @@ __device__ __forceinline__ void tmem_ld_16x256(uint32_t taddr, float* v) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_16x256_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+      "[%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
 // four 8x8 b16 matrices: register i of lane t is row t/4, 32-bit column t%4 of matrix i; lane t
@@ -174,9 +194,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t smem
       "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
@@ -370,7 +387,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const uint32_t my_slot = slot_s + h * kUOutSlotBytes;
     const int o_xg = ((32 * q) & (W - 1)) >> 2;
     const int o_img = (32 * q) / W;
-    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, shuffles, fixups, hf, emit, steps
+    long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // wait, tmem, combine+post+barrier, shuffles, fixups, hf, emit, steps, [emit split:] pack, slot wait, stage, issue
 
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const UpItem it = decode_item(item, p);
@@ -416,15 +433,25 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         mbar_wait(&bars->tmem_full[as], aphase);
         tc_fence_after();
         if constexpr (PROF) tq[1] = clock64();
-        const uint32_t tcol = tmem_base + static_cast<uint32_t>(as * kUAccStride + h * 8) +
+        // accumulator columns: [channel half][tap][8 channels] (prep_weights, transpose_io = 2)
+        const uint32_t tcol = tmem_base + static_cast<uint32_t>(as * kUAccStride + h * 72) +
                               (static_cast<uint32_t>(q * 32) << 16);
         float P[9][8];
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_16x256_x8(tcol, ra);                               // taps 0-7, pixels j = 0, 1
+          tmem_ld_16x256_x8(tcol + (16u << 16), rb);                 // taps 0-7, pixels j = 2, 3
+          tmem_ld_16x256(tcol + 64, &P[8][0]);
+          tmem_ld_16x256(tcol + 64 + (16u << 16), &P[8][4]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          tmem_ld_16x256(tcol + t * UNC, &P[t][0]);                  // pixels j = 0, 1
-          tmem_ld_16x256(tcol + t * UNC + (16u << 16), &P[t][4]);    // pixels j = 2, 3
+          for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              P[t][i] = __uint_as_float(ra[4 * t + i]);
+              P[t][4 + i] = __uint_as_float(rb[4 * t + i]);
+            }
         }
-        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
@@ -529,6 +556,8 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
               nz[4] = b4.x; nz[5] = b4.y; nz[6] = b4.z; nz[7] = b4.w;
             }
             uint32_t hw[2][4], lw[2][4];
+            long long te[7];
+            if constexpr (PROF) te[0] = clock64();
 #pragma unroll
             for (int xi = 0; xi < 2; ++xi) {
 #pragma unroll
@@ -558,17 +587,32 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
               }
             }
             // the slots are free once the previous row's stores have read them
-            if (lane == 0) tma_store_wait_read();
-            named_bar_sync(3 + q, 64);
+            if constexpr (PROF) te[1] = clock64();
+            if (lane == 0) tma_store_wait_read_n<0>();
+            named_bar_sync(kBarPair + q, 64);
+            if constexpr (PROF) te[2] = clock64();
 #pragma unroll
             for (int xi = 0; xi < 2; ++xi) {
               stmatrix_x4(st_addr[xi], hw[xi]);
               stmatrix_x4(st_addr[xi] + kUOutSlotBytes, lw[xi]);
             }
+            if constexpr (PROF) te[5] = clock64();
             fence_proxy_async_smem();
-            named_bar_sync(3 + q, 64);
+            if constexpr (PROF) te[6] = clock64();
+            named_bar_sync(kBarPair + q, 64);
+            if constexpr (PROF) te[3] = clock64();
+            // warp (q, h) issues plane h's store.  (Two dedicated store warps instead, fed through
+            // arrive/sync barrier pairs, were slower: 922 vs 830 us at layer 13.)
             if (lane == 0 && (!PROF || p.debug_nostore == 0))
               tma_store_5d(omap, my_slot, it.cg * UNC, o_xg, 0, Y, b0 + o_img);
+            if constexpr (PROF) {
+              te[4] = clock64();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) prof_acc[8 + i] += te[i + 1] - te[i];
+              prof_acc[12] += te[5] - te[2];
+              prof_acc[13] += te[6] - te[5];
+              prof_acc[14] += te[3] - te[6];
+            }
             if (img_ok && last_x && c == 0) {       // zero pad column of the output grid
               const size_t off = ((img_row0 + Y) * (Wo + 1) + Wo) * p.Cout + it.cg * UNC + h * 8;
               *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(0u, 0u, 0u, 0u);
@@ -613,9 +657,9 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     if (lane == 0) tma_store_wait_all();
     if constexpr (PROF) {
       if (lane == 0 && p.debug_prof != nullptr) {
-        long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 8;
+        long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = prof_acc[i];
+        for (int i = 0; i < 16; ++i) dst[i] = prof_acc[i];
       }
     }
   }

@@ -138,7 +138,7 @@ def weight_planes(weight, kind='fwd', scale=None):
         wsq = torch.empty((Cout, Cin), dtype=torch.float32, device=w.device)
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 0, 0, _p(hi), _p(lo), _p(wsq),
                    _stream())
-    elif kind == 'upf':        # [Cout/16][tap][16][Cin]: N = 144 tiles of the fused up-conv
+    elif kind == 'upf':        # [Cout/16][half][tap][8][Cin]: N = 144 tiles of the fused up-conv
         wsq = weight_planes(weight, 'fwd', scale)[2]
         _cabi.call('rw_prep_weights', _p(w), Cout, Cin, scale, 2, 0, _p(hi), _p(lo), None,
                    _stream())

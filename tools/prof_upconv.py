@@ -29,7 +29,7 @@ def main():
     kern = (torch.tensor([1., 3., 3., 1.])[:, None] * torch.tensor([1., 3., 3., 1.])[None, :] / 16).to(dev)
     nh = torch.empty((B * (Ho + 1) * (Ho + 1), Cout), dtype=torch.bfloat16, device=dev)
     nl = torch.empty_like(nh)
-    prof = torch.zeros(148, 8, 8, dtype=torch.int64, device=dev)
+    prof = torch.zeros(148, 8, 16, dtype=torch.int64, device=dev)
     args = (ops._p(planes.hi), ops._p(planes.lo), ops._p(u_hi), ops._p(u_lo), ops._p(dm), ops._p(kern),
             ops._p(noise), noise.stride(0), ops._p(nw), ops._p(bias), ops._p(ns), ops._p(nh), ops._p(nl),
             B, Cin, Cout, H, H)
@@ -52,6 +52,9 @@ def main():
     print('steps per epilogue warp (avg) %.1f, cycles per step %.0f' % (steps / (p[:, :, 7] > 0).sum(), tot / steps))
     for i, n in enumerate(names):
         print('  %-34s %7.0f cycles/step  %5.1f %%' % (n, p[:, :, i].sum() / steps, 100 * p[:, :, i].sum() / tot))
+    for i, n in enumerate(['FIR+activation+split', 'wait for the staging slots', 'stmatrix+fence+barrier',
+                           'TMA store issue', '   stmatrix x4', '   fence.proxy.async', '   pair barrier']):
+        print('      of the last: %-26s %7.0f cycles/step' % (n, p[:, :, 8 + i].sum() / steps))
 
 
 if __name__ == '__main__':
