@@ -504,9 +504,11 @@ def main():
                 'conv_transpose + 4x4 blur + demod + noise + bias + leaky-ReLU + next-layer planes in one '
                 'launch; FLOPs counted for the conv_transpose only)', 'kernel_launches': up_launches,
                 'kernel_ms_per_step': up_ms / K,
-                'note': 'epilogue-bound (SIMT FIR + activation behind the MMAs), see DESIGN.md §6; '
-                        'the round-1 pair conv_transpose + blur kernel took the same time with 2.3x '
-                        'the DRAM traffic'}
+                'note': 'layer 13 is epilogue-bound (SIMT FIR + activation behind the MMAs: 5.2k cycles '
+                        'per row step against 3.7k of MMAs), layers 9/11 wait for the MMAs half of the '
+                        'time (3-term split: frac <= 1/3), tools/prof_upconv.py + DESIGN.md §6; the '
+                        'round-1 pair (conv_transpose GEMM + SIMT blur) moved 2.3x the DRAM bytes of the '
+                        'layer pair'}
         if cov is not None and 'samples_per_s' in cov:
             # second half of BASELINE.json's metric: key-covariance samples/s (config 3)
             cov_tf = cov['samples_per_s'] * GFLOP_PER_COV_SAMPLE / 1e3

@@ -1033,6 +1033,84 @@ small_gemm_kernel(int B, int K, long long a_stride, float scale, float bias_mul,
   }
 }
 
+// Same jobs for B <= 32 rows (the batch-32 generation step: 8 mapping layers, styles, demod):
+// the tiled kernel above runs 8 CTAs of 16 dependent load-sync-compute rounds there (31 us per
+// mapping layer, ncu).  Here one WARP owns one output column for all rows: lanes stride over K in
+// float4, every load of the K loop is independent, the 32 per-row partial sums are reduced by
+// recursive halving (31 shuffles) so that lane b ends with row b.  8 columns per block.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(int B, int K, long long a_stride, float scale, float bias_mul, int act, float eps,
+                   const GemmJobs jobs) {
+  int l = 0;
+  const int blk = blockIdx.x;
+  while (blk >= jobs.first_block[l + 1]) ++l;
+  const int N = jobs.n_out[l];
+  const int lane = threadIdx.x & 31;
+  const int o = (blk - jobs.first_block[l]) * 8 + (threadIdx.x >> 5);
+  if (o >= N) return;                               // whole warp; no block-level sync below
+  const float* A = jobs.a[l];
+  const float* wrow = jobs.w[l] + static_cast<size_t>(o) * K;
+  float acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+  for (int k0 = lane * 4; k0 < K; k0 += 128) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + k0));
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      if (b < B) {
+        float4 a4 = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(b) * a_stride + k0));
+        if (MODE == 1) { a4.x *= a4.x; a4.y *= a4.y; a4.z *= a4.z; a4.w *= a4.w; }
+        acc[b] = fmaf(a4.w, w4.w, fmaf(a4.z, w4.z, fmaf(a4.y, w4.y, fmaf(a4.x, w4.x, acc[b]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {               // lane keeps the half whose row bit equals its own
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = upper ? acc[i + s] : acc[i];
+      const float send = upper ? acc[i] : acc[i + s];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  if (lane < B) {
+    float v;
+    if (MODE == 1) {
+      v = rsqrtf(acc[0] + eps);
+    } else {
+      v = acc[0] * scale;
+      if (jobs.bias[l]) v += __ldg(jobs.bias[l] + o) * bias_mul;
+      if (act) v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
+    }
+    jobs.out[l][static_cast<size_t>(lane) * N + o] = v;
+  }
+}
+
+// B <= 32 and float4-addressable rows: the skinny kernel; otherwise the tiled one
+template <int MODE>
+static int gemm_jobs_launch(GemmJobs& jobs, int B, int K, long long a_stride, float scale,
+                            float bias_mul, int act, float eps, cudaStream_t stream) {
+  bool skinny = B <= 32 && K % 4 == 0 && a_stride % 4 == 0;
+  for (int i = 0; i < jobs.n && skinny; ++i)
+    skinny = ((reinterpret_cast<uintptr_t>(jobs.a[i]) | reinterpret_cast<uintptr_t>(jobs.w[i])) & 15u) == 0;
+  const int cols = skinny ? 8 : 64;
+  int blocks = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    jobs.first_block[i] = blocks;
+    blocks += (jobs.n_out[i] + cols - 1) / cols;
+  }
+  jobs.first_block[jobs.n] = blocks;
+  if (skinny) {
+    skinny_gemm_kernel<MODE><<<blocks, 256, 0, stream>>>(B, K, a_stride, scale, bias_mul, act, eps, jobs);
+  } else {
+    dim3 grid(blocks, (B + 31) / 32);
+    small_gemm_kernel<MODE><<<grid, 256, 0, stream>>>(B, K, a_stride, scale, bias_mul, act, eps, jobs);
+  }
+  return check_cuda(cudaGetLastError(), MODE == 1 ? "demod gemm launch" : "styles launch");
+}
+
 // ---------------------------------------------------------------------------
 // ProgGAN leaves (reference utils/proggan.py:128-141): PixelNormLayer
 //   out[b,c,y,x] = x[b,c,y,x] / sqrt(mean_c x[b,:,y,x]^2 + 1e-8)
@@ -1290,21 +1368,15 @@ int styles_launch(const float* latent, int B, int n_latent, int K, float scale, 
   // applied to the accumulated sum here (one rounding per output instead of one per weight)
   GemmJobs jobs;
   jobs.n = n;
-  int blocks = 0;
   for (int i = 0; i < n; ++i) {
     jobs.a[i] = latent + static_cast<size_t>(lat[i]) * K;
     jobs.w[i] = w[i];
     jobs.bias[i] = bias[i];
     jobs.out[i] = out[i];
     jobs.n_out[i] = chans[i];
-    jobs.first_block[i] = blocks;
-    blocks += (chans[i] + 63) / 64;
   }
-  jobs.first_block[n] = blocks;
-  dim3 grid(blocks, (B + 31) / 32);
-  small_gemm_kernel<0><<<grid, 256, 0, stream>>>(B, K, static_cast<long long>(n_latent) * K, scale,
-                                                 bias_mul, act, 0.f, jobs);
-  return check_cuda(cudaGetLastError(), "styles launch");
+  return gemm_jobs_launch<0>(jobs, B, K, static_cast<long long>(n_latent) * K, scale, bias_mul, act,
+                             0.f, stream);
 }
 
 int pixel_norm_launch(const float* z, int B, int K, float* out, cudaStream_t stream) {
@@ -1350,7 +1422,7 @@ int demod_multi_launch(int B, float eps, int n, const float* const* style,
   for (int pass_cin = 0;;) {
     GemmJobs g;
     g.n = 0;
-    int blocks = 0, K = 0;                          // K = smallest Cin above pass_cin
+    int K = 0;                                      // K = smallest Cin above pass_cin
     for (int i = 0; i < n; ++i)
       if (kind[i] == 0 && cin[i] > pass_cin && (K == 0 || cin[i] < K)) K = cin[i];
     if (K == 0) break;
@@ -1361,14 +1433,9 @@ int demod_multi_launch(int B, float eps, int n, const float* const* style,
       g.bias[g.n] = nullptr;
       g.out[g.n] = out[i];
       g.n_out[g.n] = cout[i];
-      g.first_block[g.n] = blocks;
-      blocks += (cout[i] + 63) / 64;
       ++g.n;
     }
-    g.first_block[g.n] = blocks;
-    dim3 grid(blocks, (B + 31) / 32);
-    small_gemm_kernel<1><<<grid, 256, 0, stream>>>(B, K, K, 1.f, 0.f, 0, eps, g);
-    int rc = check_cuda(cudaGetLastError(), "demod_multi launch");
+    int rc = gemm_jobs_launch<1>(g, B, K, K, 1.f, 0.f, 0, eps, stream);
     if (rc) return rc;
     pass_cin = K;
   }

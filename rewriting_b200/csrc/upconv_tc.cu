@@ -19,22 +19,31 @@
 // (the 3-term bf16 split), so no chunk promotion is needed against the tensor core's truncating
 // fp32 accumulate (see conv_tc.cu).
 //
-// A tile is ONE image row segment per image: lane l <-> (image l / W, x = l % W), W <= 128 a
-// power of two, 128 / W images per tile.  A CTA marches down the rows of its images; the 4x4 FIR
-// needs t rows 2y-3 .. 2y+1 to emit output rows 2y-2, 2y-1 after step y, all of which depend on
-// P at rows <= y of the SAME lane (vertical direction) and of the two neighbouring lanes
-// (horizontal direction): vertical state lives in registers (three horizontally filtered rows +
-// the u = 2 taps of the previous row), horizontal neighbours come from warp shuffles (and a
-// 2 KB shared-memory mailbox across warp boundaries).  Nothing is recomputed except two warm-up
-// rows per row band.
+// A tile is ONE image row per image: 128 / W images of width W <= 128 (a power of two).  A CTA
+// marches down the rows of its images; the 4x4 FIR needs t rows 2y-3 .. 2y+1 to emit output rows
+// 2y-2, 2y-1 after step y, all of which depend on P at rows <= y of the SAME pixel (vertical
+// direction) and of the two neighbouring pixels (horizontal direction).
+//
+// Epilogue data mapping (round 2, second version).  The tile's rows are PERMUTED inside every
+// 32-pixel quarter — tile row 8 j + g holds pixel 4 g + j — which costs nothing: the tensor map
+// lists the key planes' dimensions in the order (channel, x/4 % 8, x % 4, x/32, row) and TMA fills
+// shared memory in that order.  tcgen05.ld.16x256b then hands thread (g = lane / 4, c = lane % 4)
+// the FOUR ADJACENT pixels 4g .. 4g+3 and two output channels: three of every four horizontal
+// neighbours are in the thread's own registers, the fourth comes from lane +-4 (16 shuffles per
+// step instead of 64) or, at a quarter boundary, from a 4 KB shared-memory mailbox.  Vertical state
+// (three horizontally filtered rows + the u = 2 taps of the previous row) stays in registers;
+// nothing is recomputed except two warm-up rows per row band.  Output: bf16 hi/lo words staged
+// with stmatrix ([image][X % 8][X / 8][16 channels], 32-byte swizzle: conflict-free) and written by
+// 5-d TMA stores — as LSU stores the 32-byte pieces of 64 pixels hit 64 different lines per
+// instruction and cost a third of the step.  Measured at layer 13, batch 32 (tools/prof_upconv.py,
+// profiles/): 1 258 us (one pixel x 8 channels per thread, 16-byte stores) -> 1 074 us (partner
+// exchange, 32-byte stores) -> 830 us (this mapping).
 //
 // Warp roles (384 threads = 3 warpgroups): warps 0..7 = epilogue — lane quarter q = warp % 4
 // (hardware restriction of tcgen05.ld), channel half h = warp / 4 (8 of the tile's 16 output
 // channels); warp 8 = TMA producer, warp 9 = MMA issuer (+TMEM alloc), warps 10-11 idle.  The
 // third warpgroup gives its registers back (setmaxnreg.dec 40) so that the epilogue warps can
-// hold their ~200 live values (vertical window, carried taps, per-channel constants) without
-// spilling (setmaxnreg.inc 232): ncu of the 320-thread version showed the step time set by
-// long-scoreboard stalls on spill reloads with only two epilogue warps per scheduler.
+// hold their ~200 live values without spilling (setmaxnreg.inc 232).
 #include <cstring>
 
 #include "rw_common.cuh"
