@@ -269,13 +269,92 @@ class ProgressiveGanRewriter(object):
         self.insert(goal_in, goal_out, mkey, update_callback=update_callback, niter=niter,
                     piter=piter, lr=lr)
 
-    def apply_overfit(self, request, niter=20001, lr=0.01, update_callback=None):
-        raise NotImplementedError(
-            'apply_overfit / all_weights_insert is the paper\'s all-weights baseline with a '
-            'pretrained VGG-16 perceptual loss (ganrewrite.py:171-181,300-331); it is outside '
-            'the rewrite hot path (SURVEY.md §8a18) and needs downloaded VGG weights.')
+    def apply_overfit(self, request, niter=20001, lr=0.01, update_callback=None,
+                      feature_net=None):
+        """The paper's all-weights baseline on a UI request (ganrewrite.py:171-181): paste the
+        object's RGB crop into the target image and fit EVERY generator parameter to it."""
+        o_imgnum, o_mask = request['object']
+        p_imgnum, p_mask = request['paste']
+        # In the reference the paste target and the optimised output come from the SAME forward
+        # code, so every unpasted pixel of the crop starts at a residual of exactly 0 and the L1
+        # term's subgradient there is 0.  Here a no-grad call takes the fused fast path, whose
+        # pixels differ from the layer-by-layer autograd path in the last bits (sign(1e-7) = +-1
+        # would put +-1/N of gradient on all those pixels: measured, ~1 % of every gradient norm).
+        # The target is therefore rendered by the training forward itself.
+        nethook.set_requires_grad(True, *self.model.parameters())
+        self._render_like_training = True
+        try:
+            rgb_clip, _, obj_area, _ = self.rgb_from_selection(o_imgnum, o_mask)
+            host_z, changed_rgb, bounds = self.rgbpaste_from_selection(p_imgnum, p_mask, rgb_clip,
+                                                                       obj_area)
+        finally:
+            self._render_like_training = False
+        self.all_weights_insert(changed_rgb, host_z, bounds=bounds,
+                                update_callback=update_callback, niter=niter, lr=lr,
+                                feature_net=feature_net)
 
-    all_weights_insert = apply_overfit
+    _render_like_training = False
+
+    def _whole_image(self, z):
+        """G(z) without a graph; through the autograd forward kernels when `apply_overfit` asks
+        for pixels that are bit-identical to what its optimisation loop will see."""
+        if self._render_like_training:
+            with torch.enable_grad():
+                return self.model(z).detach()
+        with torch.no_grad():
+            return self.model(z)
+
+    def perceptual_features(self, feature_net=None):
+        """VGG-16 `features` through index 20 (ganrewrite.py:303-304).  `feature_net` (a
+        torchvision VGG-16, e.g. rewriting_b200.synthetic.seeded_vgg16() where the ImageNet weights
+        cannot be downloaded) replaces the pretrained network the reference fetches."""
+        if feature_net is None:
+            import torchvision
+            try:
+                feature_net = torchvision.models.vgg16(pretrained=True)
+            except Exception as e:        # no network / no cached checkpoint
+                raise RuntimeError(
+                    'all_weights_insert needs the pretrained VGG-16 (torchvision download failed: '
+                    '%s); pass feature_net=<torchvision VGG-16 with weights loaded>' % (e,))
+        features = getattr(feature_net, 'features', feature_net)
+        VF = nethook.subsequence(features, last_layer='20').to(self.device)
+        nethook.set_requires_grad(False, VF)
+        return VF
+
+    def all_weights_insert(self, x, z, bounds=None, update_callback=None, niter=20001, lr=0.01,
+                           feature_net=None):
+        """Adam over all parameters of the generator on L1 + 1e-2 * MSE of VGG features between the
+        target image `x` and G(z), inside `bounds` (ganrewrite.py:300-331).  The generator's
+        forward and backward run on this package's kernels (the layer-level autograd ops of
+        BASELINE config 2); the VGG network is torch's own convolution, as in the reference."""
+        x, z = [self.detach(d) for d in [x, z]]
+        VF = self.perceptual_features(feature_net)
+
+        def compute_loss():
+            out = self.model(z)
+            if bounds is None:
+                gt, pred = x, out
+            else:
+                t, l, b, r = bounds
+                gt, pred = [d[:, :, t:b, l:r] for d in [x, out]]
+            return torch.nn.functional.l1_loss(gt, pred) + (
+                1e-2 * torch.nn.functional.mse_loss(VF(gt), VF(pred)))
+
+        nethook.set_requires_grad(False, self.model)
+        params = list(self.model.parameters())
+        nethook.set_requires_grad(True, *params)
+        optimizer = torch.optim.Adam(params, lr=lr)
+        for it in range(niter):
+            # fp32 like the reference: cuDNN's TF32 convolutions (torch's default on this hardware)
+            # put ~1 % of error into the VGG term's gradient
+            with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+                loss = compute_loss()
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()          # in place: bumps every parameter's _version, which is
+                                          # what the cached weight planes are keyed on
+            if update_callback is not None:
+                update_callback(it, loss)
 
     # ---------------------------------------------------------------------------- the edit
     def zero(self, context, amount=0.0):
@@ -602,8 +681,7 @@ class ProgressiveGanRewriter(object):
 
     def rgb_from_selection(self, imgnum, mask):
         area = renormalize.from_url(mask, target='pt', size=self.x_shape[2:])[0]
-        with torch.no_grad():
-            x_output = self.model(self.get_z(imgnum))
+        x_output = self._whole_image(self.get_z(imgnum))
         t, l, b, r = positive_bounding_box(area)
         return x_output[:, :, t:b, l:r], x_output, area[t:b, l:r], (t, l, b, r)
 
@@ -612,7 +690,7 @@ class ProgressiveGanRewriter(object):
             area = renormalize.from_url(mask, target='pt', size=self.x_shape[2:])[0]
             source_z = self.get_z(imgnum)
             changed_rgb, bounds = paste_clip_at_center(
-                self.model(source_z), obj_rgb, centered_location(area), obj_area)
+                self._whole_image(source_z), obj_rgb, centered_location(area), obj_area)
         return source_z, changed_rgb, bounds
 
     # ---------------------------------------------------------------------------- erase

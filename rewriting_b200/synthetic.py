@@ -22,3 +22,18 @@ def seeded_generator(size=256, seed=0, noise_weight=0.37, **kwargs):
             elif name.endswith('activate.bias'):
                 p.copy_(torch.randn(p.shape, generator=g))
     return model.eval()
+
+
+def seeded_vgg16(seed=20200701):
+    """torchvision VGG-16 with seeded random weights: the stand-in for the pretrained perceptual
+    network of `all_weights_insert` (reference ganrewrite.py:303-304) wherever the ImageNet
+    weights cannot be downloaded — tests, goldens (oracle/make_golden_overfit.py) and benches.
+    The global RNG state is left untouched."""
+    import torchvision
+    state = torch.random.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        vgg = torchvision.models.vgg16(weights=None)
+    finally:
+        torch.random.set_rng_state(state)
+    return vgg.eval()
