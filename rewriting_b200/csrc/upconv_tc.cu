@@ -404,24 +404,20 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       const int b = b0 + img_in_tile;
       const bool img_ok = b < p.B;
       const int c0 = it.cg * UNC + h * 8 + 2 * c;     // first of this thread's 2 output channels
-      float dm[2], bs[2], ns[2];
-      {
-        const size_t o = static_cast<size_t>(img_ok ? b : 0) * p.Cout + c0;
-        const float2 d2 = __ldg(reinterpret_cast<const float2*>(p.demod + o));
-        const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
-        const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.next_scale + o));
-        dm[0] = d2.x; dm[1] = d2.y;
-        bs[0] = b2.x; bs[1] = b2.y;
-        ns[0] = n2.x; ns[1] = n2.y;
-      }
+      const size_t chan_o = static_cast<size_t>(img_ok ? b : 0) * p.Cout + c0;
+      const float2 dm = __ldg(reinterpret_cast<const float2*>(p.demod + chan_o));
+      const float2 bs = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+      const float2 ns = __ldg(reinterpret_cast<const float2*>(p.next_scale + chan_o));
       // vertical state: u = 2 taps of the previous input row, and the horizontally filtered
       // t rows 2y-3 (w0), 2y-2 (w1), 2y-1 (w2); each [2 output columns][8 units]
-      float c20[8], c21[8], c22[8];
-      float w0[2][8], w1[2][8], w2[2][8];
+      // (all per-pixel quantities are float2 = the thread's channel pair: the FIRs and the
+      // activation run on packed FFMA2 / FADD2 / FMUL2, bit-identical to the scalar operations)
+      float2 c20[4], c21[4], c22[4];
+      float2 w0[2][4], w1[2][4], w2[2][4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        c20[u] = c21[u] = c22[u] = 0.f;
-        w0[0][u] = w0[1][u] = w1[0][u] = w1[1][u] = w2[0][u] = w2[1][u] = 0.f;
+      for (int j = 0; j < 4; ++j) {
+        c20[j] = c21[j] = c22[j] = make_float2(0.f, 0.f);
+        w0[0][j] = w0[1][j] = w1[0][j] = w1[1][j] = w2[0][j] = w2[1][j] = make_float2(0.f, 0.f);
       }
       const float* nrow_base = p.noise + static_cast<size_t>(img_ok ? b : 0) * p.noise_bstride + 2 * x0;
       __nv_bfloat16* out_hi = static_cast<__nv_bfloat16*>(p.next_hi);
@@ -445,21 +441,24 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         // accumulator columns: [channel half][tap][8 channels] (prep_weights, transpose_io = 2)
         const uint32_t tcol = tmem_base + static_cast<uint32_t>(as * kUAccStride + h * 72) +
                               (static_cast<uint32_t>(q * 32) << 16);
-        float P[9][8];
+        float2 P[9][4];                                              // [tap][pixel j] (e0, e1)
         {
           uint32_t ra[32], rb[32];
+          float p8[8];
           tmem_ld_16x256_x8(tcol, ra);                               // taps 0-7, pixels j = 0, 1
           tmem_ld_16x256_x8(tcol + (16u << 16), rb);                 // taps 0-7, pixels j = 2, 3
-          tmem_ld_16x256(tcol + 64, &P[8][0]);
-          tmem_ld_16x256(tcol + 64 + (16u << 16), &P[8][4]);
+          tmem_ld_16x256(tcol + 64, &p8[0]);
+          tmem_ld_16x256(tcol + 64 + (16u << 16), &p8[4]);
           tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
+          for (int t = 0; t < 8; ++t) {
+            P[t][0] = make_float2(__uint_as_float(ra[4 * t]), __uint_as_float(ra[4 * t + 1]));
+            P[t][1] = make_float2(__uint_as_float(ra[4 * t + 2]), __uint_as_float(ra[4 * t + 3]));
+            P[t][2] = make_float2(__uint_as_float(rb[4 * t]), __uint_as_float(rb[4 * t + 1]));
+            P[t][3] = make_float2(__uint_as_float(rb[4 * t + 2]), __uint_as_float(rb[4 * t + 3]));
+          }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              P[t][i] = __uint_as_float(ra[4 * t + i]);
-              P[t][4 + i] = __uint_as_float(rb[4 * t + i]);
-            }
+          for (int j = 0; j < 4; ++j) P[8][j] = make_float2(p8[2 * j], p8[2 * j + 1]);
         }
         tc_fence_before();
         __syncwarp();
@@ -467,87 +466,94 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         if constexpr (PROF) tq[2] = clock64();
         if (p.debug_p != nullptr && img_ok && y < p.H && y >= it.y_emit - 1) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float* dp = p.debug_p + ((static_cast<size_t>(b) * p.H + y) * W + x0 + (u >> 1)) * 9 * p.Cout +
-                        c0 + (u & 1);
+          for (int j = 0; j < 4; ++j) {
+            float* dp = p.debug_p + ((static_cast<size_t>(b) * p.H + y) * W + x0 + j) * 9 * p.Cout + c0;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) dp[t * p.Cout] = P[t][u];
+            for (int t = 0; t < 9; ++t) *reinterpret_cast<float2*>(dp + t * p.Cout) = P[t][j];
           }
         }
 
         // t rows E = 2y, O = 2y+1 in pixel-local pieces (see the header comment):
         //   E.e[x] = leE[x] + rE[x-1], E.o[x] = oE[x];   O.e[x] = leO[x] + rO[x-1], O.o[x] = oO[x]
-        float le[2][8], ro[2][8], od[2][8];
+        float2 le[2][4], ro[2][4], od[2][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          le[0][u] = P[0][u] + c20[u];
-          od[0][u] = P[1][u] + c21[u];
-          ro[0][u] = P[2][u] + c22[u];
-          le[1][u] = P[3][u];
-          od[1][u] = P[4][u];
-          ro[1][u] = P[5][u];
-          c20[u] = P[6][u];
-          c21[u] = P[7][u];
-          c22[u] = P[8][u];
+        for (int j = 0; j < 4; ++j) {
+          le[0][j] = __fadd2_rn(P[0][j], c20[j]);
+          od[0][j] = __fadd2_rn(P[1][j], c21[j]);
+          ro[0][j] = __fadd2_rn(P[2][j], c22[j]);
+          le[1][j] = P[3][j];
+          od[1][j] = P[4][j];
+          ro[1][j] = P[5][j];
+          c20[j] = P[6][j];
+          c21[j] = P[7][j];
+          c22[j] = P[8][j];
         }
         // mailbox across quarter boundaries: the g = 7 lanes post (ro, od) of their last pixel for
         // the right-hand quarter, the g = 0 lanes post (le, od) of their first pixel
         const uint32_t mbo = (step & 1u) * kMailBufBytes;
         if (cross) {
           if (g == 7) {
-            sts_v4(post_r + mbo, ro[0][6], ro[0][7], od[0][6], od[0][7]);
-            sts_v4(post_r + mbo + 16, ro[1][6], ro[1][7], od[1][6], od[1][7]);
+            sts_v4(post_r + mbo, ro[0][3].x, ro[0][3].y, od[0][3].x, od[0][3].y);
+            sts_v4(post_r + mbo + 16, ro[1][3].x, ro[1][3].y, od[1][3].x, od[1][3].y);
           }
           if (g == 0) {
-            sts_v4(post_l + mbo, le[0][0], le[0][1], od[0][0], od[0][1]);
-            sts_v4(post_l + mbo + 16, le[1][0], le[1][1], od[1][0], od[1][1]);
+            sts_v4(post_l + mbo, le[0][0].x, le[0][0].y, od[0][0].x, od[0][0].y);
+            sts_v4(post_l + mbo + 16, le[1][0].x, le[1][0].y, od[1][0].x, od[1][0].y);
           }
-          named_bar_sync(1 + h, 128);
         }
         if constexpr (PROF) tq[3] = clock64();
         // the only pieces that come from other threads: left (ro, od) of pixel 4g-1 (lane - 4),
-        // right (le, od) of pixel 4g+4 (lane + 4); [t row][e]
-        float Lro[2][2], Lod[2][2], Rle[2][2], Rod[2][2];
+        // right (le, od) of pixel 4g+4 (lane + 4); [t row]
+        float2 Lro[2], Lod[2], Rle[2], Rod[2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            Lro[r][e] = __shfl_up_sync(0xffffffffu, ro[r][6 + e], 4);
-            Lod[r][e] = __shfl_up_sync(0xffffffffu, od[r][6 + e], 4);
-            Rle[r][e] = __shfl_down_sync(0xffffffffu, le[r][e], 4);
-            Rod[r][e] = __shfl_down_sync(0xffffffffu, od[r][e], 4);
-          }
+        for (int r = 0; r < 2; ++r) {
+          Lro[r].x = __shfl_up_sync(0xffffffffu, ro[r][3].x, 4);
+          Lro[r].y = __shfl_up_sync(0xffffffffu, ro[r][3].y, 4);
+          Lod[r].x = __shfl_up_sync(0xffffffffu, od[r][3].x, 4);
+          Lod[r].y = __shfl_up_sync(0xffffffffu, od[r][3].y, 4);
+          Rle[r].x = __shfl_down_sync(0xffffffffu, le[r][0].x, 4);
+          Rle[r].y = __shfl_down_sync(0xffffffffu, le[r][0].y, 4);
+          Rod[r].x = __shfl_down_sync(0xffffffffu, od[r][0].x, 4);
+          Rod[r].y = __shfl_down_sync(0xffffffffu, od[r][0].y, 4);
+        }
         if constexpr (PROF) tq[6] = clock64();
+        // horizontal FIR; pixels j = 1, 2 need nothing from outside the thread and are filtered
+        // BEFORE the mailbox barrier (its wait is skew between the four quarter warps)
+        const float2 kh0 = make_float2(kh[0], kh[0]), kh1 = make_float2(kh[1], kh[1]),
+                     kh2 = make_float2(kh[2], kh[2]), kh3 = make_float2(kh[3], kh[3]);
+        float2 hf[2][2][4];                      // [t row E/O][output column 2x / 2x+1][pixel j]
+        auto hfir = [&](int r, int j, float2 l_ro, float2 l_od, float2 r_le, float2 r_od) {
+          const float2 e0 = __fadd2_rn(le[r][j], l_ro);    // t col 2x
+          const float2 e1 = __fadd2_rn(r_le, ro[r][j]);    // t col 2x+2
+          const float2 o0 = od[r][j];                      // t col 2x+1
+          hf[r][0][j] = __ffma2_rn(kh3, e1, __ffma2_rn(kh2, o0, __ffma2_rn(kh1, e0, __fmul2_rn(kh0, l_od))));
+          hf[r][1][j] = __ffma2_rn(kh3, r_od, __ffma2_rn(kh2, e1, __ffma2_rn(kh1, o0, __fmul2_rn(kh0, e0))));
+        };
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          hfir(r, 1, ro[r][0], od[r][0], le[r][2], od[r][2]);
+          hfir(r, 2, ro[r][1], od[r][1], le[r][3], od[r][3]);
+        }
+        if (cross) named_bar_sync(1 + h, 128);
         if (first_x) {                            // image edge: nothing to the left
 #pragma unroll
-          for (int r = 0; r < 2; ++r) Lro[r][0] = Lro[r][1] = Lod[r][0] = Lod[r][1] = 0.f;
+          for (int r = 0; r < 2; ++r) Lro[r] = Lod[r] = make_float2(0.f, 0.f);
         } else if (mail_l) {                      // left neighbour lives in the previous quarter
-          lds_v4(read_l + mbo, Lro[0][0], Lro[0][1], Lod[0][0], Lod[0][1]);
-          lds_v4(read_l + mbo + 16, Lro[1][0], Lro[1][1], Lod[1][0], Lod[1][1]);
+          lds_v4(read_l + mbo, Lro[0].x, Lro[0].y, Lod[0].x, Lod[0].y);
+          lds_v4(read_l + mbo + 16, Lro[1].x, Lro[1].y, Lod[1].x, Lod[1].y);
         }
         if (last_x) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r) Rle[r][0] = Rle[r][1] = Rod[r][0] = Rod[r][1] = 0.f;
+          for (int r = 0; r < 2; ++r) Rle[r] = Rod[r] = make_float2(0.f, 0.f);
         } else if (mail_r) {
-          lds_v4(read_r + mbo, Rle[0][0], Rle[0][1], Rod[0][0], Rod[0][1]);
-          lds_v4(read_r + mbo + 16, Rle[1][0], Rle[1][1], Rod[1][0], Rod[1][1]);
+          lds_v4(read_r + mbo, Rle[0].x, Rle[0].y, Rod[0].x, Rod[0].y);
+          lds_v4(read_r + mbo + 16, Rle[1].x, Rle[1].y, Rod[1].x, Rod[1].y);
         }
         if constexpr (PROF) tq[7] = clock64();
-        float hf[2][2][8];                       // [t row E/O][output column 2x / 2x+1][unit]
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float l_ro = u < 2 ? Lro[r][u & 1] : ro[r][u < 2 ? u : u - 2];
-            const float l_od = u < 2 ? Lod[r][u & 1] : od[r][u < 2 ? u : u - 2];
-            const float r_le = u >= 6 ? Rle[r][u & 1] : le[r][u >= 6 ? u : u + 2];
-            const float r_od = u >= 6 ? Rod[r][u & 1] : od[r][u >= 6 ? u : u + 2];
-            const float e0 = le[r][u] + l_ro;           // t col 2x
-            const float e1 = r_le + ro[r][u];           // t col 2x+2
-            const float o0 = od[r][u];                  // t col 2x+1
-            hf[r][0][u] = fmaf(kh[3], e1, fmaf(kh[2], o0, fmaf(kh[1], e0, kh[0] * l_od)));
-            hf[r][1][u] = fmaf(kh[3], r_od, fmaf(kh[2], e1, fmaf(kh[1], o0, kh[0] * e0)));
-          }
+          hfir(r, 0, Lro[r], Lod[r], le[r][1], od[r][1]);
+          hfir(r, 3, ro[r][2], od[r][2], Rle[r], Rod[r]);
         }
         if constexpr (PROF) tq[4] = clock64();
         if (rows_out) {
@@ -567,30 +573,29 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             uint32_t hw[2][4], lw[2][4];
             long long te[7];
             if constexpr (PROF) te[0] = clock64();
+            const float2 kv0 = make_float2(kv[0], kv[0]), kv1 = make_float2(kv[1], kv[1]),
+                         kv2 = make_float2(kv[2], kv[2]), kv3 = make_float2(kv[3], kv[3]);
 #pragma unroll
             for (int xi = 0; xi < 2; ++xi) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float nzv = nw * nz[2 * j + xi];
-                float kk[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int u = 2 * j + e;
-                  float v;
-                  if (yi == 0)
-                    v = fmaf(kv[3], hf[0][xi][u],
-                             fmaf(kv[2], w2[xi][u], fmaf(kv[1], w1[xi][u], kv[0] * w0[xi][u])));
-                  else
-                    v = fmaf(kv[3], hf[1][xi][u],
-                             fmaf(kv[2], hf[0][xi][u], fmaf(kv[1], w2[xi][u], kv[0] * w1[xi][u])));
-                  v = (v * dm[e] + nzv) + bs[e];
-                  v = fmaxf(v, 0.2f * v) * 1.4142135623730951f;
-                  kk[e] = ns[e] * v;
-                }
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(kk[0], kk[1]);
+                float2 v;
+                if (yi == 0)
+                  v = __ffma2_rn(kv3, hf[0][xi][j],
+                                 __ffma2_rn(kv2, w2[xi][j], __ffma2_rn(kv1, w1[xi][j], __fmul2_rn(kv0, w0[xi][j]))));
+                else
+                  v = __ffma2_rn(kv3, hf[1][xi][j],
+                                 __ffma2_rn(kv2, hf[0][xi][j], __ffma2_rn(kv1, w2[xi][j], __fmul2_rn(kv0, w1[xi][j]))));
+                v = __fadd2_rn(__ffma2_rn(v, dm, make_float2(nzv, nzv)), bs);
+                const float2 t02 = __fmul2_rn(v, make_float2(0.2f, 0.2f));
+                v = __fmul2_rn(make_float2(fmaxf(v.x, t02.x), fmaxf(v.y, t02.y)),
+                               make_float2(1.4142135623730951f, 1.4142135623730951f));
+                const float2 kk = __fmul2_rn(ns, v);
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(kk.x, kk.y);
                 const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
                 const __nv_bfloat162 ll = __floats2bfloat162_rn(
-                    kk[0] - __uint_as_float(hu << 16), kk[1] - __uint_as_float(hu & 0xffff0000u));
+                    kk.x - __uint_as_float(hu << 16), kk.y - __uint_as_float(hu & 0xffff0000u));
                 hw[xi][j] = hu;
                 lw[xi][j] = *reinterpret_cast<const uint32_t*>(&ll);
               }
@@ -656,10 +661,10 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int xi = 0; xi < 2; ++xi)
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            w0[xi][u] = w2[xi][u];
-            w1[xi][u] = hf[0][xi][u];
-            w2[xi][u] = hf[1][xi][u];
+          for (int j = 0; j < 4; ++j) {
+            w0[xi][j] = w2[xi][j];
+            w1[xi][j] = hf[0][xi][j];
+            w2[xi][j] = hf[1][xi][j];
           }
       }
     }
