@@ -37,7 +37,7 @@
 // 5-d TMA stores — as LSU stores the 32-byte pieces of 64 pixels hit 64 different lines per
 // instruction and cost a third of the step.  Measured at layer 13, batch 32 (tools/prof_upconv.py,
 // profiles/): 1 258 us (one pixel x 8 channels per thread, 16-byte stores) -> 1 074 us (partner
-// exchange, 32-byte stores) -> 830 us (this mapping).
+// exchange, 32-byte stores) -> 830 us (this mapping) -> 794-817 us (packed FFMA2 arithmetic).
 //
 // Warp roles (384 threads = 3 warpgroups): warps 0..7 = epilogue — lane quarter q = warp % 4
 // (hardware restriction of tcgen05.ld), channel half h = warp / 4 (8 of the tile's 16 output
