@@ -122,6 +122,16 @@ int rw_modconv_up_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi,
                         long long noise_bstride, const float* noise_w, const float* bias,
                         const float* next_scale, void* next_hi, void* next_lo, int B, int Cin,
                         int Cout, int H, int W, rw_stream_t stream);
+
+/* The same kernel as the LAYER-level op (the autograd forward of an upsampling StyledConv,
+ * reference models.py:232-289 with upsample=True): writes this layer's activation y
+ * [B, Cout, 2H, 2W] fp32 NCHW instead of the next layer's planes.  demod may be NULL (no
+ * demodulation), noise / noise_w NULL together (no noise injection), act = 0 skips bias + leaky-ReLU
+ * (bias may then be NULL). */
+int rw_modconv_up_fused_y(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                          const float* demod, const float* kernel4x4, const float* noise,
+                          long long noise_bstride, const float* noise_w, const float* bias, int act,
+                          float* y, int B, int Cin, int Cout, int H, int W, rw_stream_t stream);
 /* all modulation linears in one launch: out_l[b,c] = latent[b,lat_l,:] . (W_l[c,:]*scale) + bias_l[c]
  * (HOST arrays of n device pointers / ints; n <= 32) */
 int rw_styles(const float* latent, int B, int n_latent, int K, float scale, int n,

@@ -58,6 +58,8 @@ SIGNATURES = {
                                      c_p, c_p]),
     'rw_modconv_up_fused': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p,
                                     c_int, c_int, c_int, c_int, c_int, c_p]),
+    'rw_modconv_up_fused_y': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_int, c_p,
+                                      c_int, c_int, c_int, c_int, c_int, c_p]),
     'rw_debug_upconv_taps': (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p,
                                      c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     'rw_rowgemm': (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),

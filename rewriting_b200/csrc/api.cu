@@ -437,6 +437,25 @@ int rw_modconv_up_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi,
   return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
 }
 
+int rw_modconv_up_fused_y(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
+                          const float* demod, const float* kernel4x4, const float* noise,
+                          long long noise_bstride, const float* noise_w, const float* bias, int act,
+                          float* y, int B, int Cin, int Cout, int H, int W, rw_stream_t stream) {
+  if (!kp_hi || !kp_lo || !wt_hi || !wt_lo || !kernel4x4 || !y || (noise && (noise_bstride & 3)) ||
+      ((noise != nullptr) != (noise_w != nullptr))) {
+    set_last_error("rw_modconv_up_fused_y: bad argument");
+    return RW_ERR_BAD_ARG;
+  }
+  UpFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W;
+  p.demod = demod; p.bias = bias; p.noise = noise; p.noise_bstride = noise_bstride;
+  p.noise_w = noise_w; p.k4 = kernel4x4;
+  p.y_out = y;
+  p.act = act;
+  return upconv_fused_launch(p, kp_hi, kp_lo, wt_hi, wt_lo, stream);
+}
+
 int rw_debug_upconv_taps(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                          const float* ones_bo, const float* kernel4x4, const float* noise,
                          long long noise_bstride, const float* noise_w, const float* bias,

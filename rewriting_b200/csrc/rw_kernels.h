@@ -70,6 +70,11 @@ struct UpFusedParams {
   const float* next_scale;     // [B, Cout] style of the consuming layer
   void* next_hi;               // [B][2H+1][2W+1][Cout] bf16 planes (pad row / column zeroed)
   void* next_lo;
+  // layer-level mode (the autograd op's forward): y_out != null writes the layer's own output
+  // y [B][Cout][2H][2W] fp32 instead of the next layer's planes; demod / noise / noise_w may then
+  // be null (= 1 / no noise) and act = 0 skips bias + leaky-ReLU
+  float* y_out;
+  int act;
   int ncg, nbands, nitems;     // filled by the launcher
   float* debug_p;              // bring-up: raw tap products P[b][y][x][tap][Cout] (y < H), or null
   int debug_nostore;           // bring-up (profiling variant only): skip the plane stores

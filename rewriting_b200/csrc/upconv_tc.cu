@@ -210,7 +210,9 @@ __device__ __forceinline__ void tma_store_wait_all() {
 
 // PROF = true: bring-up variant that accumulates, per epilogue warp, the cycles spent in each phase
 // of a step (tools/prof_upconv.py) into p.debug_prof; the product launches PROF = false.
-template <bool PROF>
+// NCHW = true: the layer-level op — writes y (fp32 NCHW, this layer's activation) instead of the
+// next layer's operand planes (no staging, no TMA stores, no next-style scaling).
+template <bool PROF, bool NCHW>
 __global__ void __launch_bounds__(kUThreads, 1)
 upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     const __grid_constant__ CUtensorMap map_a_lo,
@@ -365,7 +367,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         kh[a] = __ldg(p.k4 + 15 - a) / k00;
       }
     }
-    const float nw = __ldg(p.noise_w);
+    const float nw = (!NCHW || (p.noise != nullptr && p.noise_w != nullptr)) ? __ldg(p.noise_w) : 0.f;
     uint32_t step = 0;
     // mailbox across quarter boundaries (W > 32): slot (h, q, side) = 4 lanes (c) x 8 floats
     // [t row E/O][ro|le e0, e1, od e0, e1]; double buffered by step parity
@@ -405,9 +407,11 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       const bool img_ok = b < p.B;
       const int c0 = it.cg * UNC + h * 8 + 2 * c;     // first of this thread's 2 output channels
       const size_t chan_o = static_cast<size_t>(img_ok ? b : 0) * p.Cout + c0;
-      const float2 dm = __ldg(reinterpret_cast<const float2*>(p.demod + chan_o));
-      const float2 bs = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
-      const float2 ns = __ldg(reinterpret_cast<const float2*>(p.next_scale + chan_o));
+      float2 dm = make_float2(1.f, 1.f), bs = make_float2(0.f, 0.f), ns = make_float2(1.f, 1.f);
+      if (!NCHW || p.demod != nullptr) dm = __ldg(reinterpret_cast<const float2*>(p.demod + chan_o));
+      if (!NCHW || (p.act && p.bias != nullptr)) bs = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+      if (!NCHW) ns = __ldg(reinterpret_cast<const float2*>(p.next_scale + chan_o));
+      const bool has_noise = !NCHW || (p.noise != nullptr && p.noise_w != nullptr);
       // vertical state: u = 2 taps of the previous input row, and the horizontally filtered
       // t rows 2y-3 (w0), 2y-2 (w1), 2y-1 (w2); each [2 output columns][8 units]
       // (all per-pixel quantities are float2 = the thread's channel pair: the FIRs and the
@@ -427,7 +431,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       for (int y = it.y_first; y < it.y_end; ++y, ++step) {
         const bool rows_out = (y >= it.y_emit);   // warp-, pair- and CTA-uniform
         const bool emit = rows_out && img_ok;
-        if (emit && c < 2) {                       // noise of the two output rows -> L1
+        if (emit && c < 2 && has_noise) {          // noise of the two output rows -> L1
           const float* np = nrow_base + static_cast<size_t>(2 * y - 2 + c) * Wo;
           asm volatile("prefetch.global.L1 [%0];\n" ::"l"(np));
         }
@@ -563,14 +567,15 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
           for (int yi = 0; yi < 2; ++yi) {
             const int Y = 2 * y - 2 + yi;
-            float nz[8];
-            {
+            float nz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (has_noise) {
               const float4* np = reinterpret_cast<const float4*>(nrow_base + static_cast<size_t>(Y) * Wo);
               const float4 a4 = __ldg(np), b4 = __ldg(np + 1);
               nz[0] = a4.x; nz[1] = a4.y; nz[2] = a4.z; nz[3] = a4.w;
               nz[4] = b4.x; nz[5] = b4.y; nz[6] = b4.z; nz[7] = b4.w;
             }
             uint32_t hw[2][4], lw[2][4];
+            float2 yv[2][4];                      // NCHW mode: [xi][j] activation of the channel pair
             long long te[7];
             if constexpr (PROF) te[0] = clock64();
             const float2 kv0 = make_float2(kv[0], kv[0]), kv1 = make_float2(kv[1], kv[1]),
@@ -588,17 +593,37 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                   v = __ffma2_rn(kv3, hf[1][xi][j],
                                  __ffma2_rn(kv2, hf[0][xi][j], __ffma2_rn(kv1, w2[xi][j], __fmul2_rn(kv0, w1[xi][j]))));
                 v = __fadd2_rn(__ffma2_rn(v, dm, make_float2(nzv, nzv)), bs);
-                const float2 t02 = __fmul2_rn(v, make_float2(0.2f, 0.2f));
-                v = __fmul2_rn(make_float2(fmaxf(v.x, t02.x), fmaxf(v.y, t02.y)),
-                               make_float2(1.4142135623730951f, 1.4142135623730951f));
-                const float2 kk = __fmul2_rn(ns, v);
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(kk.x, kk.y);
-                const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(
-                    kk.x - __uint_as_float(hu << 16), kk.y - __uint_as_float(hu & 0xffff0000u));
-                hw[xi][j] = hu;
-                lw[xi][j] = *reinterpret_cast<const uint32_t*>(&ll);
+                if (!NCHW || p.act) {
+                  const float2 t02 = __fmul2_rn(v, make_float2(0.2f, 0.2f));
+                  v = __fmul2_rn(make_float2(fmaxf(v.x, t02.x), fmaxf(v.y, t02.y)),
+                                 make_float2(1.4142135623730951f, 1.4142135623730951f));
+                }
+                if constexpr (NCHW) {
+                  yv[xi][j] = v;
+                } else {
+                  const float2 kk = __fmul2_rn(ns, v);
+                  const __nv_bfloat162 hh = __floats2bfloat162_rn(kk.x, kk.y);
+                  const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
+                  const __nv_bfloat162 ll = __floats2bfloat162_rn(
+                      kk.x - __uint_as_float(hu << 16), kk.y - __uint_as_float(hu & 0xffff0000u));
+                  hw[xi][j] = hu;
+                  lw[xi][j] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
               }
+            }
+            if constexpr (NCHW) {
+              // 8 consecutive output pixels (X = 2 x0 + 2 j + xi) of each channel: 32 contiguous
+              // bytes per (row, channel); the eight g lanes of a channel pair cover 256 bytes
+              if (img_ok) {
+                float* yrow = p.y_out + ((static_cast<size_t>(b) * p.Cout + c0) * Ho + Y) * Wo + 2 * x0;
+                const size_t cstride = static_cast<size_t>(Ho) * Wo;
+                *reinterpret_cast<float4*>(yrow) = make_float4(yv[0][0].x, yv[1][0].x, yv[0][1].x, yv[1][1].x);
+                *reinterpret_cast<float4*>(yrow + 4) = make_float4(yv[0][2].x, yv[1][2].x, yv[0][3].x, yv[1][3].x);
+                *reinterpret_cast<float4*>(yrow + cstride) = make_float4(yv[0][0].y, yv[1][0].y, yv[0][1].y, yv[1][1].y);
+                *reinterpret_cast<float4*>(yrow + cstride + 4) =
+                    make_float4(yv[0][2].y, yv[1][2].y, yv[0][3].y, yv[1][3].y);
+              }
+              continue;
             }
             // the slots are free once the previous row's stores have read them
             if constexpr (PROF) te[1] = clock64();
@@ -634,7 +659,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             }
           }
         }
-        if (emit && y == p.H) {                    // last step of the image: zero pad row
+        if (!NCHW && emit && y == p.H) {           // last step of the image: zero pad row
           const size_t prow = (img_row0 + Ho) * (Wo + 1);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -668,7 +693,7 @@ upconv_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (!NCHW && lane == 0) tma_store_wait_all();
     if constexpr (PROF) {
       if (lane == 0 && p.debug_prof != nullptr) {
         long long* dst = p.debug_prof + (static_cast<size_t>(blockIdx.x) * 8 + warp) * 16;
@@ -749,7 +774,7 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
   // output planes [B][Ho+1][Wo+1][Cout] seen as (channel, X / 8, X % 8, Y, image): one store = 16
   // channels of a quarter's 64 output pixels, staged as [image][X % 8][X / 8][16 ch] so that the
   // eight row addresses of a stmatrix fall into different banks (32-byte swizzle)
-  {
+  if (p.y_out == nullptr) {
     const uint64_t Wo = 2 * static_cast<uint64_t>(W), Ho = 2 * static_cast<uint64_t>(H);
     const uint64_t px = static_cast<uint64_t>(p.Cout) * 2;
     const uint64_t od[5] = {static_cast<uint64_t>(p.Cout), Wo / 8, 8, Ho + 1, static_cast<uint64_t>(p.B)};
@@ -757,6 +782,13 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
     const uint32_t ob[5] = {UNC, Wm / 4, 8u, 1u, 32u / Wm};
     if ((rc = make_tmap_nd_bf16(&mo_hi, p.next_hi, 5, od, os, ob, nullptr, 1))) return rc;
     if ((rc = make_tmap_nd_bf16(&mo_lo, p.next_lo, 5, od, os, ob, nullptr, 1))) return rc;
+  } else {                                  // layer-level mode stores y directly: maps unused
+    if ((reinterpret_cast<uintptr_t>(p.y_out) & 15u) != 0) {
+      set_last_error("upconv_fused: y must be 16-byte aligned");
+      return RW_ERR_BAD_ARG;
+    }
+    mo_hi = ma_hi;
+    mo_lo = ma_lo;
   }
   const uint64_t wrows = static_cast<uint64_t>(p.ncg) * UN;
   if ((rc = make_tmap_2d_bf16(&mw_hi, w_hi, p.Cin, wrows, static_cast<uint64_t>(p.Cin) * 2, UBK, UN)))
@@ -764,28 +796,21 @@ int upconv_fused_launch(const UpFusedParams& pin, const void* a_hi, const void* 
   if ((rc = make_tmap_2d_bf16(&mw_lo, w_lo, p.Cin, wrows, static_cast<uint64_t>(p.Cin) * 2, UBK, UN)))
     return rc;
   const int grid = p.nitems < sms ? p.nitems : sms;
-  if (p.debug_prof != nullptr) {
-    static bool attr_p = false;
-    if (!attr_p) {
-      rc = check_cuda(cudaFuncSetAttribute(upconv_fused_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemTotal),
-                      "upconv_fused smem attr");
-      if (rc) return rc;
-      attr_p = true;
+  auto launch = [&](auto kernel, bool& attr_done) -> int {
+    if (!attr_done) {
+      int e = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kUSmemTotal),
+                         "upconv_fused smem attr");
+      if (e) return e;
+      attr_done = true;
     }
-    upconv_fused_kernel<true><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, p);
+    kernel<<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, p);
     return check_cuda(cudaGetLastError(), "upconv_fused launch");
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(upconv_fused_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemTotal),
-                    "upconv_fused smem attr");
-    if (rc) return rc;
-    attr_set = true;
-  }
-  upconv_fused_kernel<false><<<grid, kUThreads, kUSmemTotal, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, p);
-  return check_cuda(cudaGetLastError(), "upconv_fused launch");
+  };
+  static bool attr_prof = false, attr_planes = false, attr_nchw = false;
+  if (p.debug_prof != nullptr) return launch(upconv_fused_kernel<true, false>, attr_prof);
+  if (p.y_out != nullptr) return launch(upconv_fused_kernel<false, true>, attr_nchw);
+  return launch(upconv_fused_kernel<false, false>, attr_planes);
 }
 
 }  // namespace rw

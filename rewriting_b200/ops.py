@@ -172,6 +172,15 @@ def demod_factors(style, wsq, eps=1e-8):
 _SEPARABLE = {}
 
 
+def up_fused_eligible(Cin, Cout, H, W, blur_kernel):
+    """Shapes the fused upsampling kernel takes (csrc/upconv_tc.cu): square power-of-two input of
+    width 4..128, Cin % 64 == 0, Cout % 16 == 0, rank-one 4x4 FIR; RW_UP_FUSED=0 turns it off."""
+    import os
+    return (os.environ.get('RW_UP_FUSED', '1') != '0' and H == W and 4 <= W <= 128 and
+            (W & (W - 1)) == 0 and Cin % 64 == 0 and Cout % 16 == 0 and
+            tuple(blur_kernel.shape) == (4, 4) and blur_is_separable(blur_kernel))
+
+
 def blur_is_separable(kernel):
     """True if the 4x4 FIR is rank one (the model's [1,3,3,1] x [1,3,3,1] always is), which the
     fused upsampling kernel requires.  One device->host read per kernel tensor version (done in
@@ -366,8 +375,19 @@ class StyledConvFunction(torch.autograd.Function):
         if nw is None:
             with_noise = False
         b = _f32c(bias.detach()) if (with_act and bias is not None) else None
-        t_up = None
-        if upsample:
+        if upsample and up_fused_eligible(Cin, Cout, H, W, blur_kernel):
+            # the whole layer in one launch (csrc/upconv_tc.cu, layer-level mode: y as fp32 NCHW);
+            # backward only needs y (the leaky-ReLU gate) and the planes
+            noise = noise_table(B, 4 * H * W, x.device) if with_noise else None
+            u_hi, u_lo, _ = wholder.planes('upf')
+            y = torch.empty((B, Cout, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+            kern = _f32c(blur_kernel)
+            _cabi.call('rw_modconv_up_fused_y', _p(planes.hi), _p(planes.lo), _p(u_hi), _p(u_lo),
+                       _p(dm) if dm is not None else None, _p(kern),
+                       _p(noise) if with_noise else None, noise.stride(0) if with_noise else 0,
+                       _p(nw) if with_noise else None, _p(b) if b is not None else None,
+                       1 if with_act else 0, _p(y), B, Cin, Cout, H, W, _stream())
+        elif upsample:
             t_up = convT3x3_planes(planes, w_hi, w_lo, Cout, dm)
             Ho, Wo = 2 * H, 2 * W
             noise = noise_table(B, Ho * Wo, x.device) if with_noise else None
