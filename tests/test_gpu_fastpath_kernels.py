@@ -192,6 +192,41 @@ def test_modconv_up_fused_vs_oracle(B, Cin, Cout, H):
     assert err < 2e-4 * max(1.0, want.abs().max().item()), err
 
 
+@pytest.mark.parametrize('B,H,demod,noise,act', [(3, 8, True, True, True), (2, 32, False, False, False),
+                                                 (2, 64, True, False, True), (5, 16, False, True, False)])
+def test_modconv_up_fused_layer_level_vs_oracle(B, H, demod, noise, act):
+    """The same kernel in its layer-level mode (rw_modconv_up_fused_y: y as fp32 NCHW, optional
+    demodulation / noise / bias + activation) — what the autograd op of an upsampling StyledConv
+    launches — against the oracle chain, through ops.styled_conv."""
+    from rewriting_b200 import ops
+    torch.manual_seed(40 + H)
+    dev = 'cuda'
+    Cin, Cout, W = 64, 32, H
+    x = torch.randn(B, Cin, H, W)
+    style = torch.randn(B, Cin) * 0.5 + 1
+    weight = torch.randn(1, Cout, Cin, 3, 3)
+    nw, bias = torch.tensor([0.37]), torch.randn(Cout)
+    kern = orc.make_kernel([1, 3, 3, 1]) * 4
+    k = style[:, :, None, None] * x
+    if demod:
+        t = orc.demod_conv(k, style, weight, True)
+    else:                                  # DemodulatedConv2dF with demodulate=False (models.py:313-319)
+        t = torch.nn.functional.conv_transpose2d(
+            k, weight.transpose(1, 2).squeeze(0) / (Cin * 9) ** 0.5, padding=0, stride=2)
+    t = orc.upfirdn2d(t, kern, pad=(1, 1))
+    Ho, Wo = 2 * H, 2 * W
+    if noise:
+        t = t + nw * orc.noise_table(B, Ho * Wo).view(B, 1, Ho, Wo)
+    want = orc.fused_leaky_relu(t, bias) if act else t
+    assert ops.up_fused_eligible(Cin, Cout, H, W, kern)
+    got = ops.styled_conv(x.to(dev), style.to(dev), torch.nn.Parameter(weight.to(dev)),
+                          nw.to(dev) if noise else None, bias.to(dev) if act else None, upsample=True,
+                          blur_kernel=kern.to(dev), demodulate=demod, with_noise=noise, with_act=act)
+    assert got.shape == want.shape
+    err = (got.cpu() - want).abs().max().item()
+    assert err < 2e-4 * max(1.0, want.abs().max().item()), err
+
+
 @pytest.mark.parametrize('B,Cin,Cout,H', [(5, 64, 256, 64), (3, 128, 512, 96)])
 def test_fused_conv_cta_pair_large_shapes_vs_oracle(B, Cin, Cout, H):
     """rw_modconv_fwd_fused on shapes with more than a wave of 256-row tiles (CTA pairs,
