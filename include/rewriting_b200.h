@@ -115,7 +115,8 @@ int rw_blur_up_fused(const float* t_cl, int B, int C, int Hin, int Win, const fl
  * Replaces the reference chain models.py:313-329 (DemodulatedConv2dF, upsample branch) -> :275-281
  * (BlurF / upfirdn2d_kernel.cu:52-137) -> :535-546 (NoiseInjectionF) -> fused_bias_act_kernel.cu
  * :27-47, without ever writing the (2H+1)x(2W+1) fp32 conv_transpose output.
- * wt_{hi,lo}: rw_prep_weights(transpose_io = 2) planes [Cout/16][9][16][Cin].  W must be a power
+ * wt_{hi,lo}: rw_prep_weights(transpose_io = 2) planes [Cout/16][2 channel halves][9 taps][8][Cin]
+ * (opaque to the caller: produced and consumed by this library only).  W must be a power
  * of two in [4, 128], Cin % 64 == 0, Cout % 16 == 0, the 4x4 kernel rank one (separable). */
 int rw_modconv_up_fused(const void* kp_hi, const void* kp_lo, const void* wt_hi, const void* wt_lo,
                         const float* demod, const float* kernel4x4, const float* noise,

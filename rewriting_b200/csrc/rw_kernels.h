@@ -80,7 +80,7 @@ struct UpFusedParams {
   int debug_nostore;           // bring-up (profiling variant only): skip the plane stores
   long long* debug_prof;       // bring-up: per (CTA, epilogue warp) cycle counters [grid][8][16], or null
 };
-// weights: bf16 hi/lo planes [Cout/16][9 taps][16][Cin]  (rw_prep_weights, transpose_io = 2)
+// weights: bf16 hi/lo planes [Cout/16][channel half][9 taps][8][Cin]  (rw_prep_weights, transpose_io = 2)
 int upconv_fused_launch(const UpFusedParams& p, const void* a_hi, const void* a_lo,
                         const void* w_hi, const void* w_lo, cudaStream_t stream);
 
