@@ -338,6 +338,39 @@ def insert_loop(weight, k, style, target, noise_w, bias, d, niter, piter=10, lr=
     return weight.detach()
 
 
+def all_weights_insert(sd, param_names, z, x, bounds, vgg_features, niter, lr=0.01,
+                       record_loss=None, record_grad0=None):
+    """ProgressiveGanRewriter.all_weights_insert (ganrewrite.py:300-331): Adam over ALL generator
+    parameters on  L1(gt, G(z)) + 1e-2 * MSE(VF(gt), VF(G(z)))  inside `bounds`, VF = VGG-16
+    `features[:21]` (nethook.subsequence(vgg.features, last_layer='20'), :303-304).
+    `sd`: state dict; `param_names`: which entries are nn.Parameters (buffers stay fixed);
+    returns the trained copies.  record_grad0 (dict) receives the first iteration's gradients."""
+    live = dict(sd)
+    params = {k: sd[k].detach().clone().requires_grad_(True) for k in param_names}
+    live.update(params)
+    VF = torch.nn.Sequential(*list(vgg_features.children())[:21])
+    for p in VF.parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.Adam([params[k] for k in param_names], lr=lr)
+    for it in range(niter):
+        out = generator_forward(live, z)
+        if bounds is None:
+            gt, pred = x, out
+        else:
+            t, l, b, r = bounds
+            gt, pred = x[:, :, t:b, l:r], out[:, :, t:b, l:r]
+        loss = F.l1_loss(gt, pred) + 1e-2 * F.mse_loss(VF(gt), VF(pred))
+        opt.zero_grad()
+        loss.backward()
+        if it == 0 and record_grad0 is not None:
+            for k in param_names:
+                record_grad0[k] = params[k].grad.detach().clone()
+        opt.step()
+        if record_loss is not None:
+            record_loss.append(float(loss.detach()))
+    return {k: v.detach() for k, v in params.items()}
+
+
 # ---------------------------------------------------------------------------------------
 # helpers shared by the tests / bench
 # ---------------------------------------------------------------------------------------
