@@ -270,7 +270,7 @@ class ProgressiveGanRewriter(object):
                     piter=piter, lr=lr)
 
     def apply_overfit(self, request, niter=20001, lr=0.01, update_callback=None,
-                      feature_net=None):
+                      feature_net=None, use_graph=None):
         """The paper's all-weights baseline on a UI request (ganrewrite.py:171-181): paste the
         object's RGB crop into the target image and fit EVERY generator parameter to it."""
         o_imgnum, o_mask = request['object']
@@ -291,7 +291,7 @@ class ProgressiveGanRewriter(object):
             self._render_like_training = False
         self.all_weights_insert(changed_rgb, host_z, bounds=bounds,
                                 update_callback=update_callback, niter=niter, lr=lr,
-                                feature_net=feature_net)
+                                feature_net=feature_net, use_graph=use_graph)
 
     _render_like_training = False
 
@@ -321,12 +321,19 @@ class ProgressiveGanRewriter(object):
         nethook.set_requires_grad(False, VF)
         return VF
 
+    GRAPH_MIN_ITERS = 16       # whole-iteration CUDA graph for all_weights_insert above this
+
     def all_weights_insert(self, x, z, bounds=None, update_callback=None, niter=20001, lr=0.01,
-                           feature_net=None):
+                           feature_net=None, use_graph=None):
         """Adam over all parameters of the generator on L1 + 1e-2 * MSE of VGG features between the
         target image `x` and G(z), inside `bounds` (ganrewrite.py:300-331).  The generator's
         forward and backward run on this package's kernels (the layer-level autograd ops of
-        BASELINE config 2); the VGG network is torch's own convolution, as in the reference."""
+        BASELINE config 2); the VGG network is torch's own convolution, as in the reference.
+
+        At batch 1 an iteration is ~600 kernel launches and launch-bound (19 ms): after three eager
+        iterations the WHOLE iteration — forward, backward, Adam step, weight-plane refresh — is
+        captured once in a CUDA graph and replayed (`use_graph`: default on for >= 16 iterations on
+        a CUDA device; any capture failure falls back to the eager loop)."""
         x, z = [self.detach(d) for d in [x, z]]
         VF = self.perceptual_features(feature_net)
 
@@ -343,8 +350,11 @@ class ProgressiveGanRewriter(object):
         nethook.set_requires_grad(False, self.model)
         params = list(self.model.parameters())
         nethook.set_requires_grad(True, *params)
-        optimizer = torch.optim.Adam(params, lr=lr)
-        for it in range(niter):
+        if use_graph is None:
+            use_graph = x.is_cuda and niter >= self.GRAPH_MIN_ITERS
+        optimizer = torch.optim.Adam(params, lr=lr, capturable=bool(use_graph))
+
+        def iteration():
             # fp32 like the reference: cuDNN's TF32 convolutions (torch's default on this hardware)
             # put ~1 % of error into the VGG term's gradient
             with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
@@ -353,8 +363,52 @@ class ProgressiveGanRewriter(object):
                 loss.backward()
                 optimizer.step()          # in place: bumps every parameter's _version, which is
                                           # what the cached weight planes are keyed on
+            return loss
+
+        it = 0
+        if use_graph:
+            it = self._all_weights_insert_graphed(iteration, params, niter, update_callback)
+        for it in range(it, niter):
+            loss = iteration()
             if update_callback is not None:
                 update_callback(it, loss)
+
+    def _all_weights_insert_graphed(self, iteration, params, niter, update_callback, warmup=3):
+        """Runs `warmup` eager iterations on a side stream, captures one iteration and replays it.
+        Returns the number of iterations done (so the caller's eager loop finishes the rest — all
+        of them after the warm-up if the capture failed)."""
+        done = 0
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for done in range(min(warmup, niter)):
+                loss = iteration()
+                if update_callback is not None:
+                    update_callback(done, loss)
+            done = min(warmup, niter)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if done >= niter:
+            return done
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph):
+                static_loss = iteration()
+        except Exception as e:                     # not capturable on this build: eager loop
+            import warnings
+            torch.cuda.synchronize()
+            warnings.warn('all_weights_insert: CUDA-graph capture failed (%s); running eagerly' % (e,))
+            return done
+        for done in range(done, niter):
+            graph.replay()
+            if update_callback is not None:
+                update_callback(done, static_loss)
+        torch.cuda.synchronize()
+        # replays change the parameters without touching their Python-side version counters:
+        # invalidate everything keyed on them (weight planes, GraphedModule captures)
+        for p in params:
+            _bump_version(p)
+        return niter
 
     # ---------------------------------------------------------------------------- the edit
     def zero(self, context, amount=0.0):

@@ -15,7 +15,7 @@ from conftest import GOLD
 pytestmark = pytest.mark.gpu
 
 
-def _run(seeded_model, z40, edit_request, niter, lr):
+def _run(seeded_model, z40, edit_request, niter, lr, return_rewriter=False):
     from rewriting_b200.rewrite import ganrewrite
     from rewriting_b200.synthetic import seeded_vgg16
     model = copy.deepcopy(seeded_model).cuda().eval()
@@ -30,6 +30,8 @@ def _run(seeded_model, z40, edit_request, niter, lr):
                 grad0[k] = p.grad.detach().float().cpu()
     gw.apply_overfit(edit_request, niter=niter, lr=lr, feature_net=seeded_vgg16(),
                      update_callback=callback)
+    if return_rewriter:
+        return gw
     upd = {k: (p.detach() - before[k]).float().cpu() for k, p in gw.model.named_parameters()}
     return losses, grad0, upd
 
@@ -70,6 +72,34 @@ def test_apply_overfit_vs_live_reference_golden(seeded_model, z40, edit_request)
         d = (upd[k] - torch.from_numpy(g['upd_%d' % i])).abs()
         assert float(d.max()) < 2e-3, (k, float(d.max()))
         assert float(d.median()) < (5e-4 if d.numel() == 1 else 5e-5), (k, float(d.median()))
+
+
+def test_graphed_iterations_match_the_eager_loop(seeded_model, z40, edit_request):
+    """Above 16 iterations the whole iteration (forward, backward, Adam, weight-plane refresh) is one
+    CUDA-graph replay: same parameters as the eager loop (capturable Adam keeps its step counter on
+    the device: last-bit differences only), and a forward afterwards sees the trained weights."""
+    from rewriting_b200.rewrite import ganrewrite
+    from rewriting_b200.synthetic import seeded_vgg16
+    vgg = seeded_vgg16()
+    out = {}
+    for mode in (False, True):
+        model = copy.deepcopy(seeded_model).cuda().eval()
+        gw = ganrewrite.SeqStyleGanRewriter(model, torch.utils.data.TensorDataset(z40), 8)
+        losses = []
+        x = gw._whole_image(z40[3:4].cuda()) * 0.5
+        gw.all_weights_insert(x, z40[3:4].cuda(), bounds=(64, 64, 192, 192), niter=24, lr=1e-4,
+                              feature_net=vgg, use_graph=mode,
+                              update_callback=lambda it, loss: losses.append(float(loss)))
+        with torch.no_grad():
+            img = gw.model(z40[3:4].cuda()).float().cpu()
+        out[mode] = (losses, {k: v.detach().float().cpu() for k, v in gw.model.named_parameters()}, img)
+    le, pe, ie = out[False]
+    lg, pg, ig = out[True]
+    assert len(le) == len(lg) == 24 and le[-1] < le[0]
+    np.testing.assert_allclose(lg, le, rtol=1e-3)     # measured 2.7e-4 at the 24th iteration
+    worst = max(float((pg[k] - pe[k]).abs().max()) for k in pe)
+    assert worst < 2e-4, worst                      # 24 steps of lr = 1e-4: updates up to 2.4e-3
+    assert float((ig - ie).abs().max()) < 2e-2 * float(ie.abs().max())
 
 
 def test_all_weights_insert_needs_a_feature_network_when_offline(seeded_model, z40, monkeypatch):

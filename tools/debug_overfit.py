@@ -41,6 +41,25 @@ def main():
     sums = np.array([float(upd[k].abs().sum()) for k in names])
     r = np.abs(sums / g['abs_update_sums'] - 1)
     print('update sums rel error: max %.2e (%s)' % (r.max(), names[int(r.argmax())]))
+    # throughput of the all-weights baseline (batch 1: forward + backward of the whole generator,
+    # VGG-16 features of the crop, Adam over 30 M parameters)
+    import copy
+    import time
+    from rewriting_b200.rewrite import ganrewrite
+    from rewriting_b200.synthetic import seeded_vgg16
+    gw = ganrewrite.SeqStyleGanRewriter(copy.deepcopy(model).cuda().eval(),
+                                        torch.utils.data.TensorDataset(z40), 8)
+    vgg = seeded_vgg16()
+    gw.apply_overfit(req, niter=3, lr=1e-4, feature_net=vgg)            # warm-up
+    for mode, n in ((False, 50), (True, 50), (True, 500)):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        gw.apply_overfit(req, niter=n, lr=1e-5, feature_net=vgg, use_graph=mode)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        print('apply_overfit (%s): %d iterations in %.2f s = %.1f it/s (incl. target rendering, VGG '
+              'setup%s)' % ('one CUDA graph per iteration' if mode else 'eager', n, dt, n / dt,
+                            ', 3 eager warm-up iterations and the capture' if mode else ''))
 
 
 if __name__ == '__main__':
