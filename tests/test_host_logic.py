@@ -274,3 +274,39 @@ def test_frechet_statistics_match_the_scipy_formula():
     f = sampling.pt_to_float255_nhwc(img)
     assert f.shape == (2, 4, 4, 3) and float(f.min()) >= 0 and float(f.max()) <= 255
     assert torch.allclose(f[0, 1, 2], ((img[0, :, 1, 2] / 2 + 0.5) * 255))
+
+
+def test_seeded_vgg16_is_deterministic_and_leaves_the_rng_alone():
+    """The stand-in for the pretrained perceptual network of all_weights_insert (tests, goldens):
+    same weights on every call and machine, global RNG state untouched."""
+    from rewriting_b200.synthetic import seeded_vgg16
+    torch.manual_seed(123)
+    before = torch.random.get_rng_state().clone()
+    a = seeded_vgg16()
+    assert torch.equal(torch.random.get_rng_state(), before)
+    b = seeded_vgg16()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert len(list(a.features.children())) == 31 and not a.training
+    assert not torch.equal(seeded_vgg16(seed=1).features[0].weight, a.features[0].weight)
+
+
+def test_up_fused_eligibility_matches_the_kernel_limits(monkeypatch):
+    """Shapes the one-kernel upsampling StyledConv takes (csrc/upconv_tc.cu: power-of-two square
+    inputs of width 4..128, Cin % 64 == 0, Cout % 16 == 0, rank-one 4x4 FIR); everything else —
+    and RW_UP_FUSED=0 — keeps the conv_transpose + blur pair."""
+    from rewriting_b200 import ops
+    k1 = torch.tensor([1., 3., 3., 1.])
+    sep = k1[:, None] * k1[None, :] / 16
+    assert ops.up_fused_eligible(512, 512, 4, 4, sep)
+    assert ops.up_fused_eligible(256, 128, 128, 128, sep)
+    assert not ops.up_fused_eligible(256, 128, 256, 256, sep)       # wider than a tile
+    assert not ops.up_fused_eligible(256, 128, 24, 24, sep)         # not a power of two
+    assert not ops.up_fused_eligible(256, 128, 32, 64, sep)         # not square
+    assert not ops.up_fused_eligible(96, 128, 32, 32, sep)          # Cin % 64
+    assert not ops.up_fused_eligible(128, 24, 32, 32, sep)          # Cout % 16
+    nonsep = sep.clone()
+    nonsep[1, 2] += 0.01
+    assert not ops.up_fused_eligible(128, 32, 32, 32, nonsep)       # FIR not rank one
+    monkeypatch.setenv('RW_UP_FUSED', '0')
+    assert not ops.up_fused_eligible(512, 512, 4, 4, sep)
